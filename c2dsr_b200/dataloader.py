@@ -1,0 +1,247 @@
+"""Batch pipeline for the C2DSR hot path (host side of SURVEY.md section 8 rows a0 and f-1/f-4).
+
+Mirrors the reference's ``dataloader.py`` interface -- ``CDSRDataset(args, mode)``,
+``get_dataloader(args)`` -- and produces *identical* field values (same consumption of
+Python's ``random`` stream, so negatives and corruptions match the reference bit for
+bit), but keeps every split as one dense int64 tensor ``[n, L]`` per field instead
+of a list of per-sample Python lists.  A ``BatchLoader`` then slices whole batches
+out of those tensors (optionally already resident on the GPU), replacing the
+reference's 14 ``LongTensor(list)`` constructions per sample.
+
+Field order (the hot path's input contract):
+  train  (dataloader.py:159-160): seq_share, seq_share_a, seq_share_b, pos, pos_a, pos_b,
+         gt_share_a, gt_share_b, gt_a, gt_b, gt_mask_a, gt_mask_b, seq_share_neg_a, seq_share_neg_b
+  eval   (dataloader.py:218-226): the first six, then idx_last_a, idx_last_b, xory_last, gt_last [n,1],
+         list_neg [n, n_neg]
+"""
+from __future__ import annotations
+
+import pickle
+import random
+from os.path import join
+from typing import List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+TRAIN_FIELDS = ("seq_share", "seq_share_a", "seq_share_b", "pos", "pos_a", "pos_b", "gt_share_a", "gt_share_b",
+                "gt_a", "gt_b", "gt_mask_a", "gt_mask_b", "seq_share_neg_a", "seq_share_neg_b")
+EVAL_FIELDS = ("seq_share", "seq_share_a", "seq_share_b", "pos", "pos_a", "pos_b", "idx_last_a", "idx_last_b",
+               "xory_last", "gt_last", "list_neg")
+
+
+def read_raw(path: str) -> List[List[int]]:
+    """Item lists sorted by timestamp with a stable sort (dataloader.py:39-58)."""
+    out = []
+    with open(path, "r", encoding="utf-8") as f:
+        for line in f:
+            pairs = [tok.split("|")[:2] for tok in line.strip().split("\t")[2:]]
+            items = np.fromiter((int(p[0]) for p in pairs), np.int64, len(pairs))
+            ts = np.fromiter((int(p[1]) for p in pairs), np.int64, len(pairs))
+            out.append(items[np.argsort(ts, kind="stable")].tolist())
+    return out
+
+
+def _split_domains(seq: np.ndarray, n_item_a: int, pad: int):
+    """Per-domain views of a mixed sequence: items kept in place, the rest PAD; 1-based positions."""
+    is_a = seq < n_item_a
+    seq_a, seq_b = np.where(is_a, seq, pad), np.where(is_a, pad, seq)
+    pos_a, pos_b = np.where(is_a, np.cumsum(is_a), 0), np.where(is_a, 0, np.cumsum(~is_a))
+    return is_a, seq_a, seq_b, pos_a, pos_b
+
+
+def _left_pad(x: np.ndarray, L: int, fill: int) -> np.ndarray:
+    out = np.full(L, fill, np.int64)
+    if len(x):
+        out[L - len(x):] = x
+    return out
+
+
+def preprocess_train(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int,
+                     rng=random) -> np.ndarray:
+    """[n_kept, 14, len_max] int64, values equal to dataloader.py:60-161 of the reference."""
+    pad = n_item_a + n_item_b
+    rows = []
+    for u in seqs:
+        if len(u) - 1 > len_max:
+            raise ValueError(f"sequence of {len(u)} items exceeds len_max+1 = {len_max + 1}")
+        u = np.asarray(u, np.int64)
+        seq, gt = u[:-1], u[1:]
+        m = len(seq)
+        is_a, seq_a, seq_b, pos_a, pos_b = _split_domains(seq, n_item_a, pad)
+        # corrupted sequences: one draw per position, in order (dataloader.py:80,85)
+        neg_a, neg_b = seq.copy(), seq.copy()
+        for i in range(m):
+            if is_a[i]:
+                neg_b[i] = rng.randint(0, n_item_a - 1)
+            else:
+                neg_a[i] = rng.randint(n_item_a, pad - 1)
+        gt_a, gt_b = np.full(m, n_item_a, np.int64), np.full(m, n_item_b, np.int64)
+        ia, ib = np.flatnonzero(is_a), np.flatnonzero(~is_a)
+        # next same-domain item is the step target; the last one takes the final target if it
+        # belongs to the domain, else it is blanked from the input (dataloader.py:96-130, Q16)
+        if len(ia):
+            gt_a[ia[:-1]] = seq[ia[1:]]
+            if gt[-1] < n_item_a:
+                gt_a[ia[-1]] = gt[-1]
+            else:
+                seq_a[ia[-1]], pos_a[ia[-1]] = pad, 0
+        mask_a = (gt_a != n_item_a).astype(np.int64)
+        if mask_a.sum() == 0:
+            continue
+        if len(ib):
+            gt_b[ib[:-1]] = seq[ib[1:]] - n_item_a
+            if gt[-1] > n_item_a:
+                gt_b[ib[-1]] = gt[-1] - n_item_a
+            else:
+                seq_b[ib[-1]], pos_b[ib[-1]] = pad, 0
+        mask_b = (gt_b != n_item_b).astype(np.int64)
+        if mask_b.sum() == 0:
+            continue
+        gt_share_a = np.where(gt < n_item_a, gt, n_item_a)
+        gt_share_b = np.where(gt >= n_item_a, gt - n_item_a, n_item_b)
+        L = len_max
+        rows.append(np.stack([
+            _left_pad(seq, L, pad), _left_pad(seq_a, L, pad), _left_pad(seq_b, L, pad),
+            _left_pad(np.arange(1, m + 1), L, 0), _left_pad(pos_a, L, 0), _left_pad(pos_b, L, 0),
+            _left_pad(gt_share_a, L, n_item_a), _left_pad(gt_share_b, L, n_item_b),
+            _left_pad(gt_a, L, n_item_a), _left_pad(gt_b, L, n_item_b),
+            _left_pad(mask_a, L, 0), _left_pad(mask_b, L, 0),
+            _left_pad(neg_a, L, pad), _left_pad(neg_b, L, pad)]))
+    return np.stack(rows) if rows else np.zeros((0, 14, len_max), np.int64)
+
+
+def preprocess_evaluate(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int,
+                        n_neg_sample: int, rng=random) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(seqs [n, 6, L], scalars [n, 4], list_neg [n, n_neg]) equal to dataloader.py:163-228."""
+    pad = n_item_a + n_item_b
+    six, four, negs = [], [], []
+    for u in seqs:
+        if len(u) - 1 > len_max:
+            raise ValueError(f"sequence of {len(u)} items exceeds len_max+1 = {len_max + 1}")
+        u = np.asarray(u, np.int64)
+        seq, gt_last = u[:-1], int(u[-1])
+        m, L = len(seq), len_max
+        is_a, seq_a, seq_b, pos_a, pos_b = _split_domains(seq, n_item_a, pad)
+        ia, ib = np.flatnonzero(is_a), np.flatnonzero(~is_a)
+        idx_last_a = int(ia[-1]) + (L - m) if len(ia) else -1
+        idx_last_b = int(ib[-1]) + (L - m) if len(ib) else -1
+        # negatives: a sample of the domain's ids without the target.  Domain B draws from
+        # range(n_item_b - n_item_a) (Q7b).  Sampling positions of an index range and shifting
+        # past the target is the same draw as sampling the reference's concatenated list.
+        if gt_last < n_item_a:
+            g, hi, dom = gt_last, n_item_a, 0
+        else:
+            g, hi, dom = gt_last - n_item_a, n_item_b - n_item_a, 1
+        n_pop = g + max(0, hi - g - 1)
+        picks = np.asarray(rng.sample(range(n_pop), n_neg_sample), np.int64)
+        negs.append(np.where(picks < g, picks, picks + 1))
+        six.append(np.stack([_left_pad(seq, L, pad), _left_pad(seq_a, L, pad), _left_pad(seq_b, L, pad),
+                             _left_pad(np.arange(1, m + 1), L, 0), _left_pad(pos_a, L, 0), _left_pad(pos_b, L, 0)]))
+        four.append([idx_last_a, idx_last_b, dom, g])
+    n = len(six)
+    return (np.stack(six) if n else np.zeros((0, 6, len_max), np.int64),
+            np.asarray(four, np.int64).reshape(n, 4),
+            np.stack(negs) if n else np.zeros((0, n_neg_sample), np.int64))
+
+
+class CDSRDataset(torch.utils.data.Dataset):
+    """Same constructor and item contract as the reference's ``CDSRDataset`` (dataloader.py:9-37,
+    230-234); holds one int64 tensor per field instead of nested lists (``self.fields``)."""
+
+    def __init__(self, args, mode: str):
+        self.mode = mode
+        self.len_max = args.len_max
+        if getattr(args, "use_raw", False):
+            seqs = read_raw(join(args.path_raw, mode + "_new.txt"))
+            if mode == "train":
+                packed = preprocess_train(seqs, args.n_item_a, args.n_item_b, args.len_max)
+                fields = [packed[:, i] for i in range(14)]
+            else:
+                six, four, neg = preprocess_evaluate(seqs, args.n_item_a, args.n_item_b, args.len_max,
+                                                     args.n_neg_sample)
+                fields = [six[:, i] for i in range(6)] + [four[:, i:i + 1] for i in range(4)] + [neg]
+            if getattr(args, "save_processed", True):
+                with open(join(args.path_data, mode + ".pkl"), "wb") as f:   # the reference's pickle layout
+                    pickle.dump([[fld[i].tolist() for fld in fields] for i in range(len(fields[0]))], f)
+        else:
+            with open(join(args.path_data, mode + ".pkl"), "rb") as f:
+                data = pickle.load(f)
+            n_f = 14 if mode == "train" else 11
+            fields = [np.asarray([row[i] for row in data], np.int64).reshape(len(data), -1) for i in range(n_f)]
+        self.fields = [torch.from_numpy(np.ascontiguousarray(x)) for x in fields]
+        self.length = len(self.fields[0])
+
+    def to(self, device, pin: bool = False):
+        """Make the whole split device-resident (or pinned) once -- 'next' row f-1."""
+        if pin and torch.device(device).type == "cpu":
+            self.fields = [x.pin_memory() for x in self.fields]
+        else:
+            self.fields = [x.to(device) for x in self.fields]
+        return self
+
+    def __len__(self):
+        return self.length
+
+    def __getitem__(self, index):
+        return tuple(x[index] for x in self.fields)
+
+
+class BatchLoader:
+    """Iterates whole batches as tuples of ``[B, ...]`` tensors sliced from ``dataset.fields``.
+
+    With ``shuffle=True`` it draws its permutation exactly as ``DataLoader(shuffle=True)``
+    does (a base seed, then a sampler seed from the default generator, then
+    ``torch.randperm`` on a private generator), so a seeded run visits the samples in the
+    reference's order (trainer.py:15, dataloader.py:254-255).
+    """
+
+    def __init__(self, dataset: CDSRDataset, batch_size: int, shuffle: bool = False, rank: int = 0,
+                 world_size: int = 1):
+        self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
+        self.rank, self.world_size = rank, world_size
+
+    def __len__(self):
+        return (len(self.dataset) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = len(self.dataset)
+        if self.shuffle:
+            torch.empty((), dtype=torch.int64).random_()                      # DataLoader's _base_seed draw
+            seed = int(torch.empty((), dtype=torch.int64).random_().item())   # RandomSampler's seed draw
+            g = torch.Generator()
+            g.manual_seed(seed)
+            order = torch.randperm(n, generator=g)
+        else:
+            order = None
+        dev = self.dataset.fields[0].device
+        for lo in range(0, n, self.batch_size):
+            hi = min(lo + self.batch_size, n)
+            if self.world_size > 1:                     # data-parallel: contiguous slice of the global batch
+                per = (hi - lo + self.world_size - 1) // self.world_size
+                lo, hi = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
+            if order is None:
+                yield tuple(x[lo:hi] for x in self.dataset.fields)
+            else:
+                idx = order[lo:hi].to(dev)
+                yield tuple(x.index_select(0, idx) for x in self.dataset.fields)
+
+
+def count_item(path: str) -> int:
+    with open(path, "r", encoding="utf-8") as f:
+        return sum(1 for _ in f)
+
+
+def get_dataloader(args):
+    """Reference signature (dataloader.py:245-272): sets args.n_item_a/b, n_item, idx_pad and
+    returns (train, val, test) loaders."""
+    p = args.path_raw if getattr(args, "use_raw", False) else args.path_data
+    args.n_item_a = count_item(join(p, "items_a.txt"))
+    args.n_item_b = count_item(join(p, "items_b.txt"))
+    args.n_item = args.n_item_a + args.n_item_b + 1
+    args.idx_pad = args.n_item - 1
+    rank, world = getattr(args, "rank", 0), getattr(args, "world_size", 1)
+    train = BatchLoader(CDSRDataset(args, "train"), args.batch_size, shuffle=True, rank=rank, world_size=world)
+    val = BatchLoader(CDSRDataset(args, "val"), args.batch_size_eval)
+    test = BatchLoader(CDSRDataset(args, "test"), args.batch_size_eval)
+    return train, val, test
