@@ -1,0 +1,166 @@
+"""ctypes binding of libc2dsr_b200.so (include/c2dsr_b200.h).
+
+The library is the only compute path of this package.  If it has not been built, or the
+current device is not a Blackwell sm_100 part, every call raises -- there is no CPU or
+PyTorch fallback.  PyTorch is used for device memory, streams and (in dist.py) NCCL.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libc2dsr_b200.so")
+_lib = None
+_lock = threading.Lock()
+
+vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b",
+                                  "lin2_w", "lin2_b", "ln1_w", "ln1_b", "ln2_w", "ln2_b")]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("p", vp), ("g", vp), ("acc", vp), ("m", vp), ("v", vp), ("vmax", vp), ("n", i64)]
+
+
+# name -> (restype, argtypes); mirrors include/c2dsr_b200.h one to one
+_DROP = [f32, u64, u64]
+_PROTOS = {
+    "c2dsr_abi_version": (i32, []),
+    "c2dsr_last_error": (C.c_char_p, []),
+    "c2dsr_device_check": (i32, []),
+    "c2dsr_gather_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32] + _DROP + [vp]),
+    "c2dsr_gather_bwd_workspace_bytes": (i64, [i64, i32]),
+    "c2dsr_gather_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32] + _DROP + [vp, i64, vp]),
+    "c2dsr_spmm": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, i32] + _DROP + [vp]),
+    "c2dsr_gemm_workspace_bytes": (i64, [i64, i64, i64]),
+    "c2dsr_gemm": (i32, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, vp, i32] + _DROP
+                   + [vp, i64, vp]),
+    "c2dsr_colsum": (i32, [vp, i64, i64, i64, vp, i32, vp]),
+    "c2dsr_wsum": (i32, [vp, vp, i64, vp, vp]),
+    "c2dsr_encoder_saved_floats": (i64, [i64, i32, i32, i32]),
+    "c2dsr_encoder_workspace_bytes": (i64, [i64, i32, i32]),
+    "c2dsr_encoder_fwd": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, f32] + _DROP
+                          + [vp, vp, vp, i64, vp]),
+    "c2dsr_encoder_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, f32] + _DROP
+                          + [vp, vp, vp, i64, vp]),
+    "c2dsr_attention_fwd": (i32, [vp, vp, i64, i32, i32, i32, i64] + _DROP + [vp, vp, vp]),
+    "c2dsr_attention_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i64] + _DROP + [vp, vp]),
+    "c2dsr_add_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, f32] + _DROP + [vp]),
+    "c2dsr_ln_bwd": (i32, [vp, vp, vp, vp, vp, i32, i64, i32, vp]),
+    "c2dsr_ln_param_grad": (i32, [vp, vp, vp, vp, vp, i64, i32, vp]),
+    "c2dsr_infomax_workspace_bytes": (i64, [i64, i32]),
+    "c2dsr_infomax_fwd": (i32, [vp] * 11 + [i64, i32, i32, f32, vp, vp, vp, vp, vp, i64, vp]),
+    "c2dsr_infomax_bwd": (i32, [vp] * 8 + [i64, i32, i32, f32] + [vp] * 9 + [vp, i64, vp]),
+    "c2dsr_score_ldz": (i64, [i64]),
+    "c2dsr_score_ce_fwd": (i32, [vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, i64, vp]),
+    "c2dsr_score_ce_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "c2dsr_score_shard": (i32, [vp, vp, vp, i64, i64, i32, vp, i64, vp, i64, vp]),
+    "c2dsr_pick_target": (i32, [vp, i64, vp, i64, i64, i64, vp, vp]),
+    "c2dsr_rank_from_scores": (i32, [vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp]),
+    "c2dsr_split_bf16": (i32, [vp, i64, i32, i64, vp, vp, vp]),
+    "c2dsr_score_tc_workspace_bytes": (i64, [i64, i64, i32]),
+    "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp]),
+    "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp]),
+    "c2dsr_adamw_amsgrad": (i32, [vp, i32, i64, f32, f32, f32, f32, f32, i32, vp]),
+    "c2dsr_axpby": (i32, [vp, vp, vp, i64, f32, f32, vp]),
+}
+EXPORTS = tuple(_PROTOS)
+
+
+class C2dsrError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load(check_device: bool = True):
+    """Load the shared library (once) and bind every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise C2dsrError(
+                        f"{_LIB_PATH} not found: build it with `python -m c2dsr_b200.build` "
+                        "(nvcc, sm_100a).  c2dsr_b200 has no CPU / PyTorch fallback.")
+                lib = C.CDLL(_LIB_PATH)
+                for name, (res, args) in _PROTOS.items():
+                    fn = getattr(lib, name)
+                    fn.restype, fn.argtypes = res, args
+                if lib.c2dsr_abi_version() != 1:
+                    raise C2dsrError("libc2dsr_b200.so ABI version mismatch; rebuild the library")
+                _lib = lib
+    if check_device:
+        _require_device()
+    return _lib
+
+
+_device_ok = False
+
+
+def _require_device():
+    global _device_ok
+    if _device_ok:
+        return
+    if not torch.cuda.is_available():
+        raise C2dsrError("c2dsr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    rc = _lib.c2dsr_device_check()
+    if rc != 0:
+        raise C2dsrError(_lib.c2dsr_last_error().decode())
+    _device_ok = True
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    lib = _lib if (_lib is not None and _device_ok) else load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise C2dsrError(f"{name} failed ({rc}): {lib.c2dsr_last_error().decode()}")
+
+
+def query(name: str, *args) -> int:
+    """Invoke a size-query entry point (no device needed)."""
+    return int(getattr(load(check_device=False), name)(*args))
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise C2dsrError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise C2dsrError("expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise C2dsrError(f"expected dtype {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Workspace:
+    """One growable scratch buffer per device; kernels on a stream run in order, so reuse is safe."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        key = torch.device(device).index or 0
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+workspace = _Workspace()

@@ -1,0 +1,156 @@
+"""``C2DSR`` module with the reference's constructor, attributes, methods and ``state_dict`` keys
+(reference: models/C2DSR.py:8-85, models/encoders.py:7-48), computing through the CUDA C-ABI
+kernels instead of torch ops.
+
+The parameter containers are the same torch modules the reference instantiates, created in the
+same order, so a seeded construction yields the reference's initial weights and a reference
+``state_dict`` loads unchanged -- including the dead ``attn_*.encoder_layer.*`` prototype copies
+(SURVEY.md Q3).  None of those containers' ``forward`` methods is used on the hot path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .graph import CsrGraph
+
+
+class GCN(nn.Module):
+    """Parameter-free propagation: mean of [h0 .. h_n_gnn], h_k = A dropout(h_{k-1})."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.dropout_gnn = args.dropout_gnn
+        self.n_gnn = args.n_gnn
+
+    def forward(self, h, graph: CsrGraph, seed: int = 0, tag: int = 0):
+        p = self.dropout_gnn if self.training else 0.0
+        return ops.GCNFn.apply(h, graph, self.n_gnn, p, seed, tag)
+
+
+class SelfAttention(nn.Module):
+    """Positional embedding + dropout + n_attn encoder layers + final LayerNorm."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.idx_pad = args.idx_pad
+        self.n_head = args.n_head
+        self.norm_first = bool(args.norm_first)
+        self.p = args.dropout_attn
+        self.register_buffer("attn_mask", nn.Transformer.generate_square_subsequent_mask(args.len_max))
+        self.dropout_attn = nn.Dropout(p=args.dropout_attn)
+        self.pos_emb = nn.Embedding(args.len_max, args.d_latent)
+        # containers only (same construction as the reference so that init and keys coincide)
+        self.encoder_layer = nn.TransformerEncoderLayer(
+            d_model=args.d_latent, nhead=args.n_head, dim_feedforward=args.d_latent, dropout=args.dropout_attn,
+            activation=nn.functional.relu, layer_norm_eps=ops.LN_EPS, batch_first=True, norm_first=args.norm_first,
+            device=args.device)
+        self.encoder = nn.TransformerEncoder(self.encoder_layer, args.n_attn,
+                                             nn.LayerNorm(args.d_latent, eps=ops.LN_EPS))
+
+    def weights(self):
+        out = []
+        for layer in self.encoder.layers:
+            out += [layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias, layer.self_attn.out_proj.weight,
+                    layer.self_attn.out_proj.bias, layer.linear1.weight, layer.linear1.bias, layer.linear2.weight,
+                    layer.linear2.bias, layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
+        return out + [self.encoder.norm.weight, self.encoder.norm.bias]
+
+    def encode(self, seq, x, seed: int, tag: int):
+        """x already holds sqrt(d) * (hi[seq] + E[seq]) + P[pos] with input dropout applied."""
+        p = self.p if self.training else 0.0
+        return ops.EncoderFn.apply(x, seq, self.n_head, self.idx_pad, self.norm_first, p, seed, tag, *self.weights())
+
+
+class C2DSR(nn.Module):
+    def __init__(self, args, adj, adj_specific):
+        super().__init__()
+        self.args = args
+        self.d_latent, self.n_item = args.d_latent, args.n_item
+        self.n_item_a, self.n_item_b = args.n_item_a, args.n_item_b
+        pad = self.n_item - 1
+
+        tables = {"embed_i": nn.Embedding(self.n_item, self.d_latent, padding_idx=pad)}
+        for name in ("embed_i_a", "embed_i_b"):
+            tables[name] = tables["embed_i"] if args.shared_item_embed else \
+                nn.Embedding(self.n_item, self.d_latent, padding_idx=pad)
+        for name, mod in tables.items():
+            setattr(self, name, mod)
+        for name in ("gnn_share", "gnn_a", "gnn_b"):
+            setattr(self, name, GCN(args))
+        for name in ("attn_share", "attn_a", "attn_b"):
+            setattr(self, name, SelfAttention(args))
+        for name, n_out in (("classifier_a", self.n_item_a), ("classifier_b", self.n_item_b), ("classifier_pad", 1)):
+            setattr(self, name, nn.Linear(self.d_latent, n_out))
+        for name in ("classifier_a", "classifier_b", "classifier_pad"):
+            nn.init.xavier_uniform_(getattr(self, name).weight)
+        for name in ("classifier_a", "classifier_b", "classifier_pad"):
+            nn.init.zeros_(getattr(self, name).bias)
+        for name in ("D_a", "D_b"):
+            setattr(self, name, nn.Bilinear(self.d_latent, self.d_latent, 1, bias=bool(args.d_bias)))
+        if args.d_bias:
+            nn.init.zeros_(self.D_a.bias)
+            nn.init.zeros_(self.D_b.bias)
+        nn.init.xavier_uniform_(self.D_a.weight)
+        nn.init.xavier_uniform_(self.D_b.weight)
+
+        # adjacency: keep what the caller passed (reference attribute names) + the CSR / CSR^T the kernels use
+        self.adj_share, self.adj_specific = adj, adj_specific
+        dev = torch.device(args.device)
+        self.graph_share = adj if isinstance(adj, CsrGraph) else CsrGraph(adj, dev)
+        self.graph_specific = adj_specific if isinstance(adj_specific, CsrGraph) else CsrGraph(adj_specific, dev)
+        self.hi_share = self.hi_a = self.hi_b = None
+        self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
+        self._calls = 0
+
+    def _apply(self, fn, *a, **k):
+        """.to()/.cuda(): the CSR graphs follow the parameters; cached propagations are dropped."""
+        out = super()._apply(fn, *a, **k)
+        dev = self.embed_i.weight.device
+        self.graph_share.to(dev)
+        self.graph_specific.to(dev)
+        self.hi_share = self.hi_a = self.hi_b = None
+        return out
+
+    # ---- dropout stream: a fresh seed per forward pass, tags per site ----
+    def _next_seed(self) -> int:
+        self._calls += 1
+        return (self._seed + 0x9E3779B97F4A7C15 * self._calls) & 0xFFFFFFFFFFFFFFFF
+
+    def convolve_graph(self):
+        """models/C2DSR.py:59-62: cache hi_share / hi_a / hi_b (kept until the next call, Q13)."""
+        s = self._next_seed()
+        self.hi_share = self.gnn_share(self.embed_i.weight, self.graph_share, s, 1)
+        self.hi_a = self.gnn_a(self.embed_i_a.weight, self.graph_specific, s, 2)
+        self.hi_b = self.gnn_b(self.embed_i_b.weight, self.graph_specific, s, 3)
+
+    def _branch(self, attn: SelfAttention, table: nn.Embedding, hi, seq, pos, seed: int, tag: int):
+        p = attn.p if self.training else 0.0
+        x = ops.GatherFn.apply(hi, table.weight, attn.pos_emb.weight, seq, pos, float(self.d_latent ** 0.5),
+                               self.n_item - 1, p, seed, tag * 2 + 1)
+        return attn.encode(seq, x, seed, tag * 2)
+
+    def forward(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b):
+        """models/C2DSR.py:64-77 -> (h_share, hx, hy), each fp32 [B, L, d]."""
+        s = self._next_seed()
+        return (self._branch(self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, s, 1),
+                self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2),
+                self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3))
+
+    def forward_share(self, seq, pos):
+        """models/C2DSR.py:79-85: the shared branch only (corrupted sequences)."""
+        return self._branch(self.attn_share, self.embed_i, self.hi_share, seq, pos, self._next_seed(), 4)
+
+    def forward_all(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b, seq_neg_a, seq_neg_b):
+        """The five branches of a training step; the three that go through ``attn_share`` (clean,
+        corrupted-A, corrupted-B) are stacked into one 3B-sequence pass.  Same values as calling
+        forward() + 2 x forward_share() (dropout masks differ per stacked row, as they would)."""
+        s = self._next_seed()
+        B = seq_share.shape[0]
+        seq3 = torch.cat((seq_share, seq_neg_a, seq_neg_b), 0)
+        pos3 = torch.cat((pos_share, pos_share, pos_share), 0)
+        h3 = self._branch(self.attn_share, self.embed_i, self.hi_share, seq3, pos3, s, 1)
+        hx = self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2)
+        hy = self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3)
+        return h3[:B], hx, hy, h3[B:2 * B], h3[2 * B:]

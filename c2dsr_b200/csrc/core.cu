@@ -1,0 +1,155 @@
+// Error plumbing, device check, small elementwise / reduction kernels and the fused AdamW-amsgrad step.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "../../include/c2dsr_b200.h"
+
+namespace c2dsr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return C2DSR_OK;
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return -(int)e;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                             int64_t n, float a, float b) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = y ? a * x[i] + b * y[i] : a * x[i];
+}
+
+// Column sums with a fixed summation order: block = 32 columns x 8 row lanes, rows strided by 8,
+// then the 8 partials are added in lane order.
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
+                              float* __restrict__ out, int accumulate) {
+    __shared__ float part[8][33];
+    int c = blockIdx.x * 32 + threadIdx.x;
+    float s = 0.f;
+    if (c < N)
+        for (int64_t r = threadIdx.y; r < M; r += 8) s += X[r * ldx + c];
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+// Single-block fixed-order weighted sum.
+__global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict__ w, int64_t n,
+                            float* __restrict__ out) {
+    __shared__ float part[1024];
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += w ? x[i] * w[i] : x[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = part[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// AdamW + amsgrad over a table of tensors.  grid = (chunks, n_tensors).
+__global__ void adamw_kernel(const c2dsr_adam_tensor* __restrict__ table, float lr, float beta1, float beta2,
+                             float eps, float wd, float inv_bc1, float sqrt_bc2) {
+    const c2dsr_adam_tensor t = table[blockIdx.y];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float decay = 1.f - lr * wd;
+    const float step_size = lr * inv_bc1;   // lr / bias_correction1
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += stride) {
+        float g = t.acc[i];
+        if (t.g) {
+            g += t.g[i];
+            t.acc[i] = g;
+        }
+        float p = t.p[i] * decay;
+        float m = t.m[i];
+        m = m + (g - m) * (1.f - beta1);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
+        float v = t.v[i] * beta2 + (1.f - beta2) * g * g; // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        float vm = fmaxf(t.vmax[i], v);
+        float denom = sqrtf(vm) / sqrt_bc2 + eps;
+        p -= step_size * (m / denom);
+        t.p[i] = p;
+        t.m[i] = m;
+        t.v[i] = v;
+        t.vmax[i] = vm;
+    }
+}
+
+}  // namespace c2dsr
+
+using namespace c2dsr;
+
+extern "C" {
+
+int c2dsr_abi_version(void) { return C2DSR_ABI_VERSION; }
+const char* c2dsr_last_error(void) { return g_err; }
+
+int c2dsr_device_check(void) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+        return -(int)e;
+    }
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) {
+        set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+        return -(int)e;
+    }
+    if (major != 10) {
+        set_error("c2dsr_b200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
+        return C2DSR_ERR_ARCH;
+    }
+    return C2DSR_OK;
+}
+
+int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream) {
+    if (n <= 0) return C2DSR_OK;
+    int blocks = (int)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+    axpby_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, out, n, a, b);
+    return check_launch("axpby");
+}
+
+int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* stream) {
+    if (N <= 0) return C2DSR_OK;
+    colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out, accumulate);
+    return check_launch("colsum");
+}
+
+int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stream) {
+    wsum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, w, n, out);
+    return check_launch("wsum");
+}
+
+int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, void* stream) {
+    if (n_tensors <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(step >= 1, "step must be >= 1");
+    double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
+    int64_t chunks = ceil_div(max_n, 256 * 4);
+    if (chunks > 148 * 8) chunks = 148 * 8;
+    if (chunks < 1) chunks = 1;
+    adamw_kernel<<<dim3((unsigned)chunks, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(
+        table_dev, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1), (float)sqrt(bc2));
+    return check_launch("adamw_amsgrad");
+}
+
+}  // extern "C"

@@ -1,0 +1,617 @@
+// K3: the SASRec-style encoder (models/encoders.py:23-33 of the reference) -- attention with the
+// reference's mask semantics, LayerNorm, residual/dropout glue, and the composite forward/backward
+// that chains them with the dense layers (gemm.cu).
+//
+// Attention semantics: query i attends key j iff j <= i AND seq[j] == PAD.  Rows
+// with no allowed key produce 0 and receive/propagate no gradient.  Sequences are short (L <= 200), so
+// attention is one warp per (sequence, head, query): lanes split the head dimension, keys are walked
+// in order with an online softmax, non-pad keys are skipped without touching memory.
+#include "common.cuh"
+#include "../../include/c2dsr_b200.h"
+
+namespace c2dsr {
+
+int gemm_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act,
+                  Dropout dr, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+
+constexpr int kMaxPerLane = 16;   // features per lane: d (or head dim) <= 512
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm family: one warp per token, lane l owns features l, l+32, ...
+// ------------------------------------------------------------------------------------------------
+__global__ void add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                  const float* __restrict__ w, const float* __restrict__ b, float* s_out,
+                                  float* out, float* __restrict__ stats, int64_t n_tok, int d, int do_ln, float eps,
+                                  Dropout dr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tok) return;
+    const int nper = (d + 31) >> 5;
+    float v[kMaxPerLane];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int f = lane + 32 * k;
+        v[k] = 0.f;
+        if (k < nper && f < d) {
+            float s = x[t * d + f];
+            if (y) s += y[t * d + f] * drop_scale(dr, (uint64_t)t * d + f);
+            v[k] = s;
+            sum += s;
+            if (s_out) s_out[t * d + f] = s;
+        }
+    }
+    if (!do_ln) {
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int f = lane + 32 * k;
+            if (k < nper && f < d) out[t * d + f] = v[k];
+        }
+        return;
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int f = lane + 32 * k;
+        if (k < nper && f < d) {
+            const float c = v[k] - mean;
+            sq += c * c;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int f = lane + 32 * k;
+        if (k < nper && f < d) out[t * d + f] = (v[k] - mean) * rstd * w[f] + b[f];
+    }
+    if (lane == 0) {
+        stats[2 * t] = mean;
+        stats[2 * t + 1] = rstd;
+    }
+}
+
+__global__ void ln_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ s,
+                              const float* __restrict__ stats, const float* __restrict__ w, float* dx_out,
+                              int accumulate, int64_t n_tok, int d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tok) return;
+    const int nper = (d + 31) >> 5;
+    const float mean = stats[2 * t], rstd = stats[2 * t + 1];
+    float g[kMaxPerLane], xh[kMaxPerLane];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int f = lane + 32 * k;
+        g[k] = 0.f;
+        xh[k] = 0.f;
+        if (k < nper && f < d) {
+            xh[k] = (s[t * d + f] - mean) * rstd;
+            g[k] = d_out[t * d + f] * w[f];
+            c1 += g[k];
+            c2 += g[k] * xh[k];
+        }
+    }
+    c1 = warp_sum(c1) / (float)d;
+    c2 = warp_sum(c2) / (float)d;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int f = lane + 32 * k;
+        if (k < nper && f < d) {
+            const float ds = rstd * (g[k] - c1 - xh[k] * c2);
+            dx_out[t * d + f] = accumulate ? dx_out[t * d + f] + ds : ds;
+        }
+    }
+}
+
+// d_w[f] += sum_t d_out[t,f] * xhat[t,f];  d_b[f] += sum_t d_out[t,f].  Fixed order (see colsum_kernel).
+__global__ void ln_param_grad_kernel(const float* __restrict__ d_out, const float* __restrict__ s,
+                                     const float* __restrict__ stats, float* d_w, float* d_b, int64_t n_tok, int d) {
+    __shared__ float pw[8][33], pb[8][33];
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    float sw = 0.f, sb = 0.f;
+    if (f < d) {
+        for (int64_t t = threadIdx.y; t < n_tok; t += 8) {
+            const float go = d_out[t * d + f];
+            sw += go * (s[t * d + f] - stats[2 * t]) * stats[2 * t + 1];
+            sb += go;
+        }
+    }
+    pw[threadIdx.y][threadIdx.x] = sw;
+    pb[threadIdx.y][threadIdx.x] = sb;
+    __syncthreads();
+    if (threadIdx.y == 0 && f < d) {
+        float a = 0.f, c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a += pw[k][threadIdx.x];
+            c += pb[k][threadIdx.x];
+        }
+        d_w[f] += a;
+        d_b[f] += c;
+    }
+}
+
+// out = in * dropout mask (same index space as the forward site)
+__global__ void drop_mul_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, Dropout dr) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] * drop_scale(dr, (uint64_t)i);
+}
+
+// backward of fd = drop(relu(pre)):  d_pre = d_fd * (fd > 0 ? 1/(1-p) : 0), in place on d_fd
+__global__ void relu_drop_bwd_kernel(float* __restrict__ d_fd, const float* __restrict__ fd, int64_t n,
+                                     float inv_keep) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d_fd[i] = fd[i] > 0.f ? d_fd[i] * inv_keep : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention
+// ------------------------------------------------------------------------------------------------
+struct AttnShape {
+    int64_t n_seq;
+    int L, d, H, dh;
+    int64_t pad;
+    float scale;
+};
+
+__device__ __forceinline__ float lane_dot(const float (&a)[kMaxPerLane], const float* __restrict__ b, int dh, int nper,
+                                          int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        if (k < nper && e < dh) s += a[k] * b[e];
+    }
+    return warp_sum(s);
+}
+
+__global__ void attn_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ seq, AttnShape sh,
+                                Dropout dr, float* __restrict__ o, float* __restrict__ lse) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= sh.n_seq * sh.H * sh.L) return;
+    const int i = (int)(w % sh.L);
+    const int h = (int)((w / sh.L) % sh.H);
+    const int64_t b = w / ((int64_t)sh.L * sh.H);
+    const int nper = (sh.dh + 31) >> 5;
+    const int64_t ld = 3 * (int64_t)sh.d;
+    const int64_t ti = b * sh.L + i;
+    float q[kMaxPerLane], acc[kMaxPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        q[k] = (k < nper && e < sh.dh) ? qkv[ti * ld + h * sh.dh + e] : 0.f;
+        acc[k] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j <= i; ++j) {
+        const int64_t tj = b * sh.L + j;
+        if (seq[tj] != sh.pad) continue;                                   // warp-uniform
+        const float* kj = qkv + tj * ld + sh.d + h * sh.dh;
+        const float* vj = kj + sh.d;
+        const float s = lane_dot(q, kj, sh.dh, nper, lane) * sh.scale;
+        const float m_new = fmaxf(m, s);
+        const float corr = expf(m - m_new);                                // exp(-inf) = 0 on the first key
+        const float pe = expf(s - m_new);
+        l = l * corr + pe;
+        const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * sh.L + i) * sh.L + j);
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < sh.dh) acc[k] = acc[k] * corr + pe * keep * vj[e];
+        }
+        m = m_new;
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        if (k < nper && e < sh.dh) o[ti * sh.d + h * sh.dh + e] = acc[k] * inv;
+    }
+    if (lane == 0) lse[ti * sh.H + h] = l > 0.f ? m + logf(l) : INFINITY;  // +inf => p = exp(s - lse) = 0
+}
+
+// First half of the warps: dq for one query.  Second half: dk, dv for one key.  No atomics.
+__global__ void attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o,
+                                const float* __restrict__ lse, const float* __restrict__ d_o,
+                                const int64_t* __restrict__ seq, AttnShape sh, Dropout dr, float* __restrict__ d_qkv) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_q = sh.n_seq * sh.H * sh.L;
+    if (w >= 2 * n_q) return;
+    const bool key_role = w >= n_q;
+    if (key_role) w -= n_q;
+    const int r = (int)(w % sh.L);                        // query index i or key index j
+    const int h = (int)((w / sh.L) % sh.H);
+    const int64_t b = w / ((int64_t)sh.L * sh.H);
+    const int nper = (sh.dh + 31) >> 5;
+    const int64_t ld = 3 * (int64_t)sh.d;
+    const int64_t tr = b * sh.L + r;
+    const int hoff = h * sh.dh;
+    float a0[kMaxPerLane], a1[kMaxPerLane], g0[kMaxPerLane], g1[kMaxPerLane];
+
+    if (!key_role) {
+        // a0 = q_i, a1 = d_o_i, g0 = dq accumulator
+        float dsum = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            const bool ok = k < nper && e < sh.dh;
+            a0[k] = ok ? qkv[tr * ld + hoff + e] : 0.f;
+            a1[k] = ok ? d_o[tr * sh.d + hoff + e] : 0.f;
+            g0[k] = 0.f;
+            if (ok) dsum += a1[k] * o[tr * sh.d + hoff + e];
+        }
+        const float D = warp_sum(dsum);
+        const float lse_i = lse[tr * sh.H + h];
+        for (int j = 0; j <= r; ++j) {
+            const int64_t tj = b * sh.L + j;
+            if (seq[tj] != sh.pad) continue;
+            const float* kj = qkv + tj * ld + sh.d + hoff;
+            const float* vj = kj + sh.d;
+            const float s = lane_dot(a0, kj, sh.dh, nper, lane) * sh.scale;
+            const float p = expf(s - lse_i);
+            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * sh.L + r) * sh.L + j);
+            const float dP = lane_dot(a1, vj, sh.dh, nper, lane) * keep;
+            const float dS = p * (dP - D) * sh.scale;
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+                const int e = lane + 32 * k;
+                if (k < nper && e < sh.dh) g0[k] += dS * kj[e];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < sh.dh) d_qkv[tr * ld + hoff + e] = g0[k];
+        }
+        return;
+    }
+
+    // key role: a0 = k_j, a1 = v_j, g0 = dk, g1 = dv
+    const bool allowed = seq[tr] == sh.pad;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        const bool ok = allowed && k < nper && e < sh.dh;
+        a0[k] = ok ? qkv[tr * ld + sh.d + hoff + e] : 0.f;
+        a1[k] = ok ? qkv[tr * ld + 2 * sh.d + hoff + e] : 0.f;
+        g0[k] = 0.f;
+        g1[k] = 0.f;
+    }
+    if (allowed) {
+        for (int i = r; i < sh.L; ++i) {
+            const int64_t ti = b * sh.L + i;
+            const float* qi = qkv + ti * ld + hoff;
+            const float* doi = d_o + ti * sh.d + hoff;
+            const float* oi = o + ti * sh.d + hoff;
+            const float lse_i = lse[ti * sh.H + h];
+            const float s = lane_dot(a0, qi, sh.dh, nper, lane) * sh.scale;
+            const float p = expf(s - lse_i);
+            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * sh.L + i) * sh.L + r);
+            float dd = 0.f;
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+                const int e = lane + 32 * k;
+                if (k < nper && e < sh.dh) dd += doi[e] * oi[e];
+            }
+            const float D = warp_sum(dd);
+            const float dP = lane_dot(a1, doi, sh.dh, nper, lane) * keep;
+            const float dS = p * (dP - D) * sh.scale;
+            const float pk = p * keep;
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+                const int e = lane + 32 * k;
+                if (k < nper && e < sh.dh) {
+                    g0[k] += dS * qi[e];
+                    g1[k] += pk * doi[e];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        if (k < nper && e < sh.dh) {
+            d_qkv[tr * ld + sh.d + hoff + e] = g0[k];
+            d_qkv[tr * ld + 2 * sh.d + hoff + e] = g1[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers shared by the C entry points and the composite
+// ------------------------------------------------------------------------------------------------
+static int launch_add_ln(const float* x, const float* y, const float* w, const float* b, float* s_out, float* out,
+                         float* stats, int64_t n_tok, int d, int do_ln, float eps, Dropout dr, cudaStream_t st) {
+    add_ln_fwd_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(x, y, w, b, s_out, out, stats, n_tok, d, do_ln,
+                                                                     eps, dr);
+    return check_launch("add_ln_fwd");
+}
+static int launch_ln_bwd(const float* d_out, const float* s, const float* stats, const float* w, float* dx_out,
+                         int accumulate, int64_t n_tok, int d, cudaStream_t st) {
+    ln_bwd_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(d_out, s, stats, w, dx_out, accumulate, n_tok, d);
+    return check_launch("ln_bwd");
+}
+static int launch_ln_param(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
+                           int64_t n_tok, int d, cudaStream_t st) {
+    ln_param_grad_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(d_out, s, stats, d_w, d_b, n_tok, d);
+    return check_launch("ln_param_grad");
+}
+static AttnShape make_shape(int64_t n_seq, int L, int d, int H, int64_t pad) {
+    AttnShape sh{n_seq, L, d, H, d / H, pad, 1.f / sqrtf((float)(d / H))};
+    return sh;
+}
+static int launch_attn_fwd(const float* qkv, const int64_t* seq, AttnShape sh, Dropout dr, float* o, float* lse,
+                           cudaStream_t st) {
+    const int64_t warps = sh.n_seq * sh.H * sh.L;
+    attn_fwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, seq, sh, dr, o, lse);
+    return check_launch("attention_fwd");
+}
+static int launch_attn_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
+                           AttnShape sh, Dropout dr, float* d_qkv, cudaStream_t st) {
+    const int64_t warps = 2 * sh.n_seq * sh.H * sh.L;
+    attn_bwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+    return check_launch("attention_bwd");
+}
+static int launch_colsum_acc(const float* X, int64_t M, int64_t N, float* out, cudaStream_t st) {
+    return c2dsr_colsum(X, N, M, N, out, 1, st);
+}
+static unsigned ew_blocks(int64_t n) {
+    int64_t b = ceil_div(n, 256);
+    return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16);
+}
+
+// saved-activation layout of one layer (floats)
+struct LayerSaved {
+    float *xin, *qkv, *lse, *o, *s1, *st1, *x1, *fd, *s2, *st2;
+};
+static int64_t layer_floats(int64_t T, int d, int H) { return T * (9 * (int64_t)d + H + 4); }
+static LayerSaved carve(float* base, int64_t T, int d, int H) {
+    LayerSaved s;
+    float* p = base;
+    s.xin = p; p += T * d;
+    s.qkv = p; p += T * 3 * d;
+    s.lse = p; p += T * H;
+    s.o = p; p += T * d;
+    s.s1 = p; p += T * d;
+    s.st1 = p; p += T * 2;
+    s.x1 = p; p += T * d;
+    s.fd = p; p += T * d;
+    s.s2 = p; p += T * d;
+    s.st2 = p; p += T * 2;
+    return s;
+}
+constexpr int64_t kGemmWsBytes = 16ll << 20;
+
+}  // namespace c2dsr
+
+using namespace c2dsr;
+
+#define RUN(expr)              \
+    do {                       \
+        int rc_ = (expr);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+extern "C" {
+
+int c2dsr_add_ln_fwd(const float* x, const float* y, const float* w, const float* b, float* s_out, float* out,
+                     float* stats, int64_t n_tok, int d, int do_ln, float eps, float p, uint64_t seed, uint64_t tag,
+                     void* stream) {
+    if (n_tok <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(d > 0 && d <= 32 * kMaxPerLane, "d must be in (0, 512]");
+    return launch_add_ln(x, y, w, b, s_out, out, stats, n_tok, d, do_ln, eps, make_dropout(p, seed, tag),
+                         (cudaStream_t)stream);
+}
+
+int c2dsr_ln_bwd(const float* d_out, const float* s, const float* stats, const float* w, float* dx_out,
+                 int accumulate, int64_t n_tok, int d, void* stream) {
+    if (n_tok <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(d > 0 && d <= 32 * kMaxPerLane, "d must be in (0, 512]");
+    return launch_ln_bwd(d_out, s, stats, w, dx_out, accumulate, n_tok, d, (cudaStream_t)stream);
+}
+
+int c2dsr_ln_param_grad(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
+                        int64_t n_tok, int d, void* stream) {
+    if (n_tok <= 0) return C2DSR_OK;
+    return launch_ln_param(d_out, s, stats, d_w, d_b, n_tok, d, (cudaStream_t)stream);
+}
+
+int c2dsr_attention_fwd(const float* qkv, const int64_t* seq, int64_t n_seq, int L, int d, int n_head,
+                        int64_t pad_idx, float p, uint64_t seed, uint64_t tag, float* o, float* lse, void* stream) {
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(n_head > 0 && d % n_head == 0 && d / n_head <= 32 * kMaxPerLane, "bad head configuration");
+    return launch_attn_fwd(qkv, seq, make_shape(n_seq, L, d, n_head, pad_idx), make_dropout(p, seed, tag), o, lse,
+                           (cudaStream_t)stream);
+}
+
+int c2dsr_attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
+                        int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, float p, uint64_t seed,
+                        uint64_t tag, float* d_qkv, void* stream) {
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(n_head > 0 && d % n_head == 0 && d / n_head <= 32 * kMaxPerLane, "bad head configuration");
+    return launch_attn_bwd(qkv, o, lse, d_o, seq, make_shape(n_seq, L, d, n_head, pad_idx),
+                           make_dropout(p, seed, tag), d_qkv, (cudaStream_t)stream);
+}
+
+int64_t c2dsr_encoder_saved_floats(int64_t n_tok, int d, int n_head, int n_layers) {
+    return n_layers * layer_floats(n_tok, d, n_head) + n_tok * ((int64_t)d + 2);
+}
+
+int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head) {
+    (void)n_head;
+    return 7 * n_tok * (int64_t)d * 4 + kGemmWsBytes + 1024;
+}
+
+int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                      const float* x, const int64_t* seq, int64_t n_seq, int L, int d, int n_head, int64_t pad_idx,
+                      int norm_first, float eps, float p, uint64_t seed, uint64_t tag, float* out, float* saved,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
+    C2DSR_REQUIRE(n_head > 0 && d % n_head == 0, "d must be divisible by n_head");
+    const int64_t T = n_seq * L;
+    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head)) {
+        set_error("encoder_fwd: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ybuf = (float*)workspace;
+    void* gws = (char*)workspace + 7 * T * (int64_t)d * 4;
+    const Dropout none = make_dropout(0.f, 0, 0);
+    const AttnShape sh = make_shape(n_seq, L, d, n_head, pad_idx);
+    const int64_t lf = layer_floats(T, d, n_head);
+    float* xlast = saved + n_layers * lf;
+    float* stf = xlast + T * d;
+    {
+        float* first = n_layers > 0 ? carve(saved, T, d, n_head).xin : xlast;
+        cudaMemcpyAsync(first, x, T * (int64_t)d * 4, cudaMemcpyDeviceToDevice, st);
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        const LayerSaved s = carve(saved + l * lf, T, d, n_head);
+        const c2dsr_layer_weights& w = layers[l];
+        float* next = l + 1 < n_layers ? carve(saved + (l + 1) * lf, T, d, n_head).xin : xlast;
+        const uint64_t tb = tag * 1024 + (uint64_t)l * 8;
+        const float* attn_in = s.xin;
+        if (norm_first) {
+            RUN(launch_add_ln(s.xin, nullptr, w.ln1_w, w.ln1_b, nullptr, s.s1, s.st1, T, d, 1, eps, none, st));
+            attn_in = s.s1;
+        }
+        RUN(gemm_dispatch(0, 1, T, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, s.qkv, 3 * d, w.in_proj_b, 0, none,
+                          gws, kGemmWsBytes, st));
+        RUN(launch_attn_fwd(s.qkv, seq, sh, make_dropout(p, seed, tb + 0), s.o, s.lse, st));
+        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, s.o, d, w.out_proj_w, d, 0.f, ybuf, d, w.out_proj_b, 0, none, gws,
+                          kGemmWsBytes, st));
+        const float* ffn_in;
+        if (norm_first) {
+            RUN(launch_add_ln(s.xin, ybuf, nullptr, nullptr, nullptr, s.x1, nullptr, T, d, 0, eps,
+                              make_dropout(p, seed, tb + 1), st));
+            RUN(launch_add_ln(s.x1, nullptr, w.ln2_w, w.ln2_b, nullptr, s.s2, s.st2, T, d, 1, eps, none, st));
+            ffn_in = s.s2;
+        } else {
+            RUN(launch_add_ln(s.xin, ybuf, w.ln1_w, w.ln1_b, s.s1, s.x1, s.st1, T, d, 1, eps,
+                              make_dropout(p, seed, tb + 1), st));
+            ffn_in = s.x1;
+        }
+        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, ffn_in, d, w.lin1_w, d, 0.f, s.fd, d, w.lin1_b, 1,
+                          make_dropout(p, seed, tb + 2), gws, kGemmWsBytes, st));
+        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, s.fd, d, w.lin2_w, d, 0.f, ybuf, d, w.lin2_b, 0, none, gws,
+                          kGemmWsBytes, st));
+        if (norm_first) {
+            RUN(launch_add_ln(s.x1, ybuf, nullptr, nullptr, nullptr, next, nullptr, T, d, 0, eps,
+                              make_dropout(p, seed, tb + 3), st));
+        } else {
+            RUN(launch_add_ln(s.x1, ybuf, w.ln2_w, w.ln2_b, s.s2, next, s.st2, T, d, 1, eps,
+                              make_dropout(p, seed, tb + 3), st));
+        }
+    }
+    RUN(launch_add_ln(xlast, nullptr, lnf_w, lnf_b, nullptr, out, stf, T, d, 1, eps, none, st));
+    return C2DSR_OK;
+}
+
+int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads* grads, int n_layers,
+                      const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,
+                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, float eps, float p,
+                      uint64_t seed, uint64_t tag, const float* saved_c, float* dx, void* workspace,
+                      int64_t workspace_bytes, void* stream) {
+    (void)eps;
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
+    const int64_t T = n_seq * L;
+    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head)) {
+        set_error("encoder_bwd: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* saved = const_cast<float*>(saved_c);
+    const int64_t Td = T * (int64_t)d;
+    float* g = (float*)workspace;        // gradient w.r.t. the current layer output / input
+    float* ds = g + Td;
+    float* dy = ds + Td;
+    float* dfd = dy + Td;
+    float* dqkv = dfd + Td;              // [T, 3d]
+    void* gws = (char*)workspace + 7 * Td * 4;
+    const Dropout none = make_dropout(0.f, 0, 0);
+    const AttnShape sh = make_shape(n_seq, L, d, n_head, pad_idx);
+    const int64_t lf = layer_floats(T, d, n_head);
+    float* xlast = saved + n_layers * lf;
+    float* stf = xlast + Td;
+    const bool has_drop = p > 0.f && p < 1.f;
+    const float inv_keep = has_drop ? 1.f / (1.f - p) : 1.f;
+
+    RUN(launch_ln_param(d_out, xlast, stf, d_lnf_w, d_lnf_b, T, d, st));
+    RUN(launch_ln_bwd(d_out, xlast, stf, lnf_w, g, 0, T, d, st));
+
+    for (int l = n_layers - 1; l >= 0; --l) {
+        const LayerSaved s = carve(saved + l * lf, T, d, n_head);
+        const c2dsr_layer_weights& w = layers[l];
+        const c2dsr_layer_grads& gw = grads[l];
+        const uint64_t tb = tag * 1024 + (uint64_t)l * 8;
+        auto masked = [&](const float* src, uint64_t site) -> const float* {
+            if (!has_drop) return src;
+            drop_mul_kernel<<<ew_blocks(Td), 256, 0, st>>>(src, dy, Td, make_dropout(p, seed, tb + site));
+            return dy;
+        };
+        // ---- feed-forward block ----
+        const float* d_s2;          // gradient at the output of the FFN residual sum
+        if (norm_first) {
+            d_s2 = g;               // x2 = x1 + drop(y2): the sum is the layer output
+        } else {
+            RUN(launch_ln_param(g, s.s2, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
+            RUN(launch_ln_bwd(g, s.s2, s.st2, w.ln2_w, ds, 0, T, d, st));
+            d_s2 = ds;
+        }
+        const float* d_y2 = masked(d_s2, 3);
+        const float* ffn_in = norm_first ? s.s2 : s.x1;
+        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y2, d, s.fd, d, 1.f, gw.lin2_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(launch_colsum_acc(d_y2, T, d, gw.lin2_b, st));
+        RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y2, d, w.lin2_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        relu_drop_bwd_kernel<<<ew_blocks(Td), 256, 0, st>>>(dfd, s.fd, Td, inv_keep);
+        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, dfd, d, ffn_in, d, 1.f, gw.lin1_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(launch_colsum_acc(dfd, T, d, gw.lin1_b, st));
+        // gradient w.r.t. x1 (post-norm: d_s2 + d_pre W1; pre-norm: g + LN2^T(d_pre W1))
+        float* d_x1;
+        if (norm_first) {
+            RUN(gemm_dispatch(0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(launch_ln_param(ds, s.x1, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
+            RUN(launch_ln_bwd(ds, s.x1, s.st2, w.ln2_w, g, 1, T, d, st));
+            d_x1 = g;
+        } else {
+            RUN(gemm_dispatch(0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 1.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            d_x1 = ds;
+        }
+        // ---- attention block ----
+        const float* d_s1;
+        if (norm_first) {
+            d_s1 = d_x1;            // x1 = xin + drop(y)
+        } else {
+            RUN(launch_ln_param(d_x1, s.s1, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
+            RUN(launch_ln_bwd(d_x1, s.s1, s.st1, w.ln1_w, g, 0, T, d, st));
+            d_s1 = g;
+        }
+        const float* d_y = masked(d_s1, 1);
+        const float* attn_in = norm_first ? s.s1 : s.xin;
+        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y, d, s.o, d, 1.f, gw.out_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(launch_colsum_acc(d_y, T, d, gw.out_proj_b, st));
+        RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y, d, w.out_proj_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(launch_attn_bwd(s.qkv, s.o, s.lse, dfd, seq, sh, make_dropout(p, seed, tb + 0), dqkv, st));
+        RUN(gemm_dispatch(1, 0, 3 * d, d, T, 1.f, dqkv, 3 * d, attn_in, d, 1.f, gw.in_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(launch_colsum_acc(dqkv, T, 3 * d, gw.in_proj_b, st));
+        if (norm_first) {
+            RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(launch_ln_param(ds, s.xin, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
+            RUN(launch_ln_bwd(ds, s.xin, s.st1, w.ln1_w, g, 1, T, d, st));
+        } else {
+            RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 1.f, g, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        }
+        // g now holds the gradient w.r.t. this layer's input
+    }
+    cudaMemcpyAsync(dx, g, Td * 4, cudaMemcpyDeviceToDevice, st);
+    return check_launch("encoder_bwd");
+}
+
+}  // extern "C"

@@ -172,6 +172,15 @@ class CDSRDataset(torch.utils.data.Dataset):
         self.fields = [torch.from_numpy(np.ascontiguousarray(x)) for x in fields]
         self.length = len(self.fields[0])
 
+    @classmethod
+    def from_fields(cls, fields, mode: str, len_max: int):
+        """Wrap already-preprocessed field tensors (train: 14 x [n, L]; eval: 6 x [n, L], 4 x [n, 1], [n, n_neg])."""
+        self = cls.__new__(cls)
+        self.mode, self.len_max = mode, len_max
+        self.fields = [torch.as_tensor(x).contiguous() for x in fields]
+        self.length = len(self.fields[0])
+        return self
+
     def to(self, device, pin: bool = False):
         """Make the whole split device-resident (or pinned) once -- 'next' row f-1."""
         if pin and torch.device(device).type == "cpu":

@@ -101,6 +101,11 @@ class CsrGraph:
         self.rowptr, self.col, self.val = self._csr(idx[0], idx[1], val, n, device)
         self.t_rowptr, self.t_col, self.t_val = self._csr(idx[1], idx[0], val, n, device)
 
+    def to(self, device):
+        for name in ("rowptr", "col", "val", "t_rowptr", "t_col", "t_val"):
+            setattr(self, name, getattr(self, name).to(device))
+        return self
+
     @staticmethod
     def _csr(row, col, val, n, device):
         order = torch.argsort(row * n + col, stable=True)

@@ -1,0 +1,113 @@
+"""Experiment driver with the reference's command line (main.py:14-148): every flag of the
+reference is accepted with the same default and meaning (the ones the reference ignores --
+max_grad_norm, lr_decay, n_lr_decay, decay_epoch, disable_embed_l2, len_max -- are ignored here
+too).  Extra flags of this implementation are listed last.
+
+    python -m c2dsr_b200.main --data fk --cuda 0
+    torchrun --nproc-per-node 8 -m c2dsr_b200.main --data mb      # data-parallel + sharded eval
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+from os.path import join
+
+import numpy as np
+import torch
+
+from . import dist as cdist
+from .metrics import BENCHMARKS, MAPPING_DATASET, cal_score
+from .noter import Noter
+from .trainer import Trainer
+
+FLAGS = [
+    # (name, kwargs) -- reference flags, main.py:18-65
+    ("--data", dict(type=str, default="fk")), ("--len_rec", dict(type=int, default=10)),
+    ("--use_raw", dict(action="store_true")), ("--n_neg_sample", dict(type=int, default=999)),
+    ("--zip_ee", dict(action="store_true")), ("--d_latent", dict(type=int, default=128)),
+    ("--disable_embed_l2", dict(action="store_true")), ("--shared_item_embed", dict(action="store_true")),
+    ("--d_bias", dict(action="store_true")), ("--n_gnn", dict(type=int, default=1)),
+    ("--dropout_gnn", dict(type=float, default=0.2)), ("--n_attn", dict(type=int, default=1)),
+    ("--n_head", dict(type=int, default=1)), ("--dropout_attn", dict(type=float, default=0.2)),
+    ("--norm_first", dict(action="store_true")), ("--lr", dict(type=float, default=1e-3)),
+    ("--lr_decay", dict(type=float, default=0.1)), ("--l2", dict(type=float, default=5e-4)),
+    ("--lr_gamma", dict(type=float, default=0.5)), ("--lr_step", dict(type=int, default=10)),
+    ("--n_lr_decay", dict(type=int, default=5)), ("--decay_epoch", dict(type=int, default=5)),
+    ("--max_grad_norm", dict(type=float, default=5.0)), ("--len_max", dict(type=int, default=15)),
+    ("--lambda_loss", dict(type=float, default=0.7)), ("--cuda", dict(type=str, default="0")),
+    ("--seed", dict(type=int, default=3407)), ("--n_epoch", dict(type=int, default=200)),
+    ("--batch_size", dict(type=int, default=512)), ("--batch_size_eval", dict(type=int, default=2048)),
+    ("--num_workers", dict(type=int, default=1)), ("--es_patience", dict(type=int, default=10)),
+    # this implementation
+    ("--full_catalog", dict(action="store_true", help="rank against every item of the domain, not list_neg")),
+    ("--save_processed", dict(action="store_true", help="with --use_raw: write the *.pkl files")),
+]
+
+
+def parse_args(argv=None):
+    parser = argparse.ArgumentParser(description="C2DSR on B200")
+    for name, kw in FLAGS:
+        parser.add_argument(name, **kw)
+    args = parser.parse_args(argv)
+    args.dataset = MAPPING_DATASET[args.data]
+    args.benchmark = BENCHMARKS[args.data]
+    args.len_max = 30 if args.dataset == "Entertainment-Education" else 15        # main.py:71
+    if args.cuda == "cpu":
+        raise SystemExit("c2dsr_b200 has no CPU path: run the reference for --cuda cpu")
+    rank, world, local_rank = cdist.init_from_env("nccl")
+    args.rank, args.world_size = rank, world
+    args.device = torch.device("cuda", local_rank if world > 1 else int(args.cuda))
+    torch.cuda.set_device(args.device)
+    args.path_root = os.getcwd()
+    args.path_data = join(args.path_root, "data", args.dataset)
+    args.path_raw = join(args.path_root, "data", "raw", args.dataset)
+    args.path_ckpt = join(args.path_root, "checkpoints")
+    args.path_log = join(args.path_root, "log")
+    for p in (args.path_ckpt, args.path_log):
+        os.makedirs(p, exist_ok=True)
+    if args.use_raw and not os.path.exists(args.path_raw):
+        raise FileNotFoundError(f"Selected raw dataset {args.dataset} does not exist..")
+    if not args.use_raw and not os.path.exists(args.path_data):
+        raise FileNotFoundError(f"Selected processed dataset {args.dataset} does not exist..")
+    return args
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    torch.cuda.manual_seed_all(args.seed)
+    np.random.seed(args.seed)
+
+    noter = Noter(args)
+    trainer = Trainer(args, noter)
+    scheduler = torch.optim.lr_scheduler.StepLR(trainer.optimizer, step_size=args.lr_step, gamma=args.lr_gamma)
+
+    epoch, stale, best_val = 0, 0, -1.0
+    res_test = [0.0] * 13
+    lr_seen = args.lr
+    for epoch in range(1, args.n_epoch + 1):
+        noter.log_msg(f"\n[Epoch {epoch}]")
+        res_val = cal_score(*trainer.run_epoch(), args.benchmark)
+        scheduler.step()                               # the stepped scheduler (main.py:103,115; Q12)
+        noter.log_evaluate("valid", res_val)
+        if res_val[0] > best_val:                      # model selection on the mean improvement
+            best_val, stale = res_val[0], 0
+            res_test = cal_score(*trainer.run_test(), args.benchmark)
+            noter.log_evaluate("test", res_test)
+        else:
+            stale += 1
+            noter.log_msg(f"\t| es    | {stale} / {args.es_patience} |")
+            if stale >= args.es_patience:
+                break
+        lr_now = trainer.optimizer.param_groups[0]["lr"]
+        if lr_now != lr_seen:
+            noter.log_msg(f"\t| lr    | from {lr_seen:.2e} | to {lr_now:.2e} |")
+            lr_seen = lr_now
+    noter.log_final_result(epoch, best_val, res_test)
+    return best_val, res_test
+
+
+if __name__ == "__main__":
+    main()

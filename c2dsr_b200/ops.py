@@ -1,0 +1,293 @@
+"""Host-side operators of the hot path: thin ``torch.autograd.Function`` wrappers that hand raw
+device pointers to the C-ABI kernels (include/c2dsr_b200.h).  No arithmetic happens here except
+allocation of outputs; all functions raise if the CUDA library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import LayerWeights, call, ptr, query, stream, workspace
+
+F32, I64, I32 = torch.float32, torch.int64, torch.int32
+LN_EPS = 1e-8          # models/encoders.py:24-27 of the reference
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    return t.contiguous() if t.dtype == F32 else t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# K2: GCN propagation (models/encoders.py:42-48)
+# ------------------------------------------------------------------------------------------------
+def spmm(rowptr, col, val, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_mode=0, p=0.0,
+         seed=0, tag=0):
+    n, d = X.shape
+    out = torch.empty_like(X) if out is None else out
+    call("c2dsr_spmm", ptr(rowptr, I32), ptr(col, I32), ptr(val, F32), ptr(X, F32), ptr(Y), ptr(Z), ptr(out, F32),
+         n, d, alpha, beta, gamma, drop_mode, p, seed, tag, stream())
+    return out
+
+
+class GCNFn(torch.autograd.Function):
+    """hi = mean([E, A drop(E), A drop(A drop(E)), ...]) with A in CSR; backward uses the CSR of A^T."""
+
+    @staticmethod
+    def forward(ctx, E, graph, n_gnn: int, p: float, seed: int, tag: int):
+        E = _f(E)
+        ctx.graph, ctx.n_gnn, ctx.p, ctx.seed, ctx.tag = graph, n_gnn, p, seed, tag
+        if n_gnn == 0:
+            return E.clone()
+        c = 1.0 / (n_gnn + 1)
+        g = graph
+        h, acc = E, E
+        for j in range(1, n_gnn + 1):
+            t = tag * 16 + j
+            if j == n_gnn:
+                return spmm(g.rowptr, g.col, g.val, h, Y=acc, alpha=c, beta=c, drop_mode=1, p=p, seed=seed, tag=t)
+            h = spmm(g.rowptr, g.col, g.val, h, drop_mode=1, p=p, seed=seed, tag=t)
+            nxt = torch.empty_like(h)
+            call("c2dsr_axpby", ptr(h), ptr(acc), ptr(nxt), h.numel(), 1.0, 1.0, stream())
+            acc = nxt
+
+    @staticmethod
+    def backward(ctx, d_hi):
+        g, k, p, seed, tag = ctx.graph, ctx.n_gnn, ctx.p, ctx.seed, ctx.tag
+        d_hi = _f(d_hi)
+        if k == 0:
+            return d_hi, None, None, None, None, None
+        c = 1.0 / (k + 1)
+        # g_{j-1} = c d_hi + m_j .* (A^T g_j), g_k = c d_hi
+        cur = spmm(g.t_rowptr, g.t_col, g.t_val, d_hi, Y=d_hi, alpha=c, beta=c, drop_mode=2, p=p, seed=seed,
+                   tag=tag * 16 + k)
+        for j in range(k - 1, 0, -1):
+            cur = spmm(g.t_rowptr, g.t_col, g.t_val, cur, Y=d_hi, alpha=1.0, beta=c, drop_mode=2, p=p, seed=seed,
+                       tag=tag * 16 + j)
+        return cur, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K1: branch input (models/C2DSR.py:65-71, models/encoders.py:30-31)
+# ------------------------------------------------------------------------------------------------
+class GatherFn(torch.autograd.Function):
+    """x = drop(sqrt(d) * (hi[seq] + E[seq]) + P[pos]);  seq, pos int64 of any shape -> [..., d]."""
+
+    @staticmethod
+    def forward(ctx, hi, E, P, seq, pos, scale: float, pad_idx: int, p: float, seed: int, tag: int):
+        hi, E, P = _f(hi), _f(E), _f(P)
+        seq_c, pos_c = seq.contiguous(), pos.contiguous()
+        d = E.shape[1]
+        x = torch.empty(*seq.shape, d, device=E.device, dtype=F32)
+        call("c2dsr_gather_fwd", ptr(hi), ptr(E), ptr(P), ptr(seq_c, I64), ptr(pos_c, I64), ptr(x), seq_c.numel(),
+             d, scale, p, seed, tag, stream())
+        ctx.save_for_backward(seq_c, pos_c)
+        ctx.cfg = (hi.shape, P.shape, scale, pad_idx, p, seed, tag)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        seq, pos = ctx.saved_tensors
+        (n_rows, d), p_shape, scale, pad_idx, p, seed, tag = ctx.cfg
+        dx = _f(dx)
+        d_hi = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
+        d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
+        d_P = torch.zeros(p_shape, device=dx.device, dtype=F32)
+        n = seq.numel()
+        nb = query("c2dsr_gather_bwd_workspace_bytes", n, d)
+        ws = workspace.get(nb, dx.device)
+        call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, pad_idx, scale,
+             p, seed, tag, ptr(ws), ws.numel(), stream())
+        return d_hi, d_E, d_P, None, None, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K3: encoder (models/encoders.py:23-33)
+# ------------------------------------------------------------------------------------------------
+_LAYER_FIELDS = ("in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+                 "ln1_w", "ln1_b", "ln2_w", "ln2_b")
+
+
+def _layer_table(tensors: Sequence[torch.Tensor], n_layers: int):
+    arr = (LayerWeights * max(n_layers, 1))()
+    for l in range(n_layers):
+        for k, name in enumerate(_LAYER_FIELDS):
+            setattr(arr[l], name, ptr(tensors[12 * l + k], F32))
+    return arr
+
+
+class EncoderFn(torch.autograd.Function):
+    """x [n_seq, L, d], seq [n_seq, L] -> encoder output.  ``weights`` = 12 tensors per layer in the
+    order of _LAYER_FIELDS, then the final LayerNorm weight and bias."""
+
+    @staticmethod
+    def forward(ctx, x, seq, n_head: int, pad_idx: int, norm_first: bool, p: float, seed: int, tag: int, *weights):
+        x = _f(x)
+        seq = seq.contiguous()
+        n_seq, L, d = x.shape
+        n_layers = (len(weights) - 2) // 12
+        w = [_f(t) for t in weights]
+        T = n_seq * L
+        saved = torch.empty(query("c2dsr_encoder_saved_floats", T, d, n_head, n_layers), device=x.device, dtype=F32)
+        out = torch.empty_like(x)
+        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head), x.device)
+        table = _layer_table(w, n_layers)
+        call("c2dsr_encoder_fwd", C.addressof(table), n_layers, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), n_seq,
+             L, d, n_head, pad_idx, int(norm_first), LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws), ws.numel(),
+             stream())
+        ctx.save_for_backward(saved, seq, *w)
+        ctx.cfg = (n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        saved, seq, *w = ctx.saved_tensors
+        n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers = ctx.cfg
+        d_out = _f(d_out)
+        grads = [torch.zeros_like(t) for t in w]
+        dx = torch.empty(n_seq, L, d, device=d_out.device, dtype=F32)
+        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", n_seq * L, d, n_head), d_out.device)
+        wt, gt = _layer_table(w, n_layers), _layer_table(grads, n_layers)
+        call("c2dsr_encoder_bwd", C.addressof(wt), C.addressof(gt), n_layers, ptr(w[-2]), ptr(grads[-2]),
+             ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), LN_EPS, p, seed,
+             tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
+        return (dx, None, None, None, None, None, None, None, *grads)
+
+
+# ------------------------------------------------------------------------------------------------
+# K5: infomax (trainer.py:85-119)
+# ------------------------------------------------------------------------------------------------
+class InfomaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h_share, hx, hy, h_neg_a, h_neg_b, W_a, W_b, bias_a, bias_b, gt_mask_a, gt_mask_b,
+                inv_batch: float):
+        hs = [_f(t) for t in (h_share, hx, hy, h_neg_a, h_neg_b)]
+        B, L, d = hs[0].shape
+        Wa, Wb = _f(W_a).view(d, d), _f(W_b).view(d, d)
+        ma, mb = gt_mask_a.contiguous(), gt_mask_b.contiguous()
+        dev = hs[0].device
+        pooled = torch.empty(6, B, d, device=dev, dtype=F32)
+        U = torch.empty(4, B, d, device=dev, dtype=F32)
+        sims = torch.empty(4, B, device=dev, dtype=F32)
+        loss = torch.empty((), device=dev, dtype=F32)
+        ws = workspace.get(query("c2dsr_infomax_workspace_bytes", B, d), dev)
+        call("c2dsr_infomax_fwd", *(ptr(t) for t in hs), ptr(ma, I64), ptr(mb, I64), ptr(Wa), ptr(Wb),
+             ptr(bias_a), ptr(bias_b), B, L, d, inv_batch, ptr(pooled), ptr(U), ptr(sims), ptr(loss), ptr(ws),
+             ws.numel(), stream())
+        ctx.save_for_backward(pooled, U, sims, ma, mb, Wa, Wb)
+        ctx.cfg = (B, L, d, inv_batch, bias_a is not None, W_a.shape)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        pooled, U, sims, ma, mb, Wa, Wb = ctx.saved_tensors
+        B, L, d, inv_batch, has_bias, w_shape = ctx.cfg
+        dev = pooled.device
+        d_loss = _f(d_loss).reshape(1)
+        dh = [torch.empty(B, L, d, device=dev, dtype=F32) for _ in range(5)]
+        dWa, dWb = torch.zeros(d, d, device=dev, dtype=F32), torch.zeros(d, d, device=dev, dtype=F32)
+        dba = torch.zeros(1, device=dev, dtype=F32) if has_bias else None
+        dbb = torch.zeros(1, device=dev, dtype=F32) if has_bias else None
+        ws = workspace.get(query("c2dsr_infomax_workspace_bytes", B, d), dev)
+        call("c2dsr_infomax_bwd", ptr(d_loss), ptr(pooled), ptr(U), ptr(sims), ptr(ma), ptr(mb), ptr(Wa), ptr(Wb), B,
+             L, d, inv_batch, *(ptr(t) for t in dh), ptr(dWa), ptr(dWb), ptr(dba), ptr(dbb), ptr(ws), ws.numel(),
+             stream())
+        return (*dh, dWa.view(w_shape), dWb.view(w_shape), dba, dbb, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# K4a: classifier + cross-entropy (trainer.py:131-152)
+# ------------------------------------------------------------------------------------------------
+_GEMM_WS = 64 << 20
+
+
+def gemm(ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, alpha=1.0, beta=0.0, bias=None, act=0):
+    ws = workspace.get(_GEMM_WS, Cm.device)
+    call("c2dsr_gemm", ta, tb, M, N, K, alpha, ptr(A), lda, ptr(B), ldb, beta, ptr(Cm), ldc, ptr(bias), act, 0.0, 0,
+         0, ptr(ws), ws.numel(), stream())
+    return Cm
+
+
+class ScoreCEFn(torch.autograd.Function):
+    """sum_m rowscale[m] * CE([H W^T + b | Hpad wpad^T + bpad][m], gt[m]) with ignore_index = N.
+
+    H, Hpad [M, d]; W [N, d]; gt [M] int64 in [0, N]; rowscale [M] fp32 (device)."""
+
+    @staticmethod
+    def forward(ctx, H, Hpad, W, b, wpad, bpad, gt, rowscale):
+        H, Hpad, W, b, wpad, bpad = (_f(t) for t in (H, Hpad, W, b, wpad, bpad))
+        gt, rowscale = gt.contiguous(), _f(rowscale)
+        M, d = H.shape
+        N = W.shape[0]
+        dev = H.device
+        ldz = query("c2dsr_score_ldz", N)
+        zpad = torch.empty(M, device=dev, dtype=F32)
+        gemm(0, 1, M, 1, d, Hpad, d, wpad, d, zpad, 1, bias=bpad)
+        Z = torch.empty(M, ldz, device=dev, dtype=F32)
+        lse = torch.empty(M, device=dev, dtype=F32)
+        loss_row = torch.empty(M, device=dev, dtype=F32)
+        ws = workspace.get(_GEMM_WS, dev)
+        call("c2dsr_score_ce_fwd", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, ptr(Z), ptr(lse),
+             ptr(loss_row), ptr(ws), ws.numel(), stream())
+        loss = torch.empty((), device=dev, dtype=F32)
+        call("c2dsr_wsum", ptr(loss_row), ptr(rowscale), M, ptr(loss), stream())
+        ctx.save_for_backward(H, Hpad, W, wpad, gt, rowscale, zpad, Z, lse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        H, Hpad, W, wpad, gt, rowscale, zpad, Z, lse = ctx.saved_tensors
+        M, d = H.shape
+        N = W.shape[0]
+        dev = H.device
+        coef = (rowscale * d_loss).contiguous()
+        dH = torch.empty(M, d, device=dev, dtype=F32)
+        dW = torch.zeros(N, d, device=dev, dtype=F32)
+        db = torch.zeros(N, device=dev, dtype=F32)
+        dzpad = torch.empty(M, device=dev, dtype=F32)
+        ws = workspace.get(_GEMM_WS, dev)
+        call("c2dsr_score_ce_bwd", ptr(H), ptr(W), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d, ptr(Z), ptr(dH),
+             ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
+        dHpad = torch.empty(M, d, device=dev, dtype=F32)
+        gemm(0, 0, M, d, 1, dzpad, 1, wpad, d, dHpad, d)                 # outer product dzpad (x) wpad
+        dwpad = torch.empty(1, d, device=dev, dtype=F32)
+        gemm(1, 0, 1, d, M, dzpad, 1, Hpad, d, dwpad, d)                 # dzpad^T Hpad
+        dbpad = torch.empty(1, device=dev, dtype=F32)
+        call("c2dsr_wsum", ptr(dzpad), None, M, ptr(dbpad), stream())
+        return dH, dHpad, dW, db, dwpad, dbpad, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# K4b: scoring + rank counting (trainer.py:168-179)
+# ------------------------------------------------------------------------------------------------
+def score_shard(Q, W, bias) -> torch.Tensor:
+    """S[n_q, lds] = Q W^T + b (fp32 FFMA path; lds = n_shard rounded up to 4)."""
+    Q, W, bias = _f(Q), _f(W), _f(bias)
+    n_q, d = Q.shape
+    n = W.shape[0]
+    lds = (n + 3) // 4 * 4
+    S = torch.empty(n_q, lds, device=Q.device, dtype=F32)
+    ws = workspace.get(_GEMM_WS, Q.device)
+    call("c2dsr_score_shard", ptr(Q), ptr(W), ptr(bias), n_q, n, d, ptr(S), lds, ptr(ws), ws.numel(), stream())
+    return S
+
+
+def pick_target(S, gt, n0: int, n1: int) -> torch.Tensor:
+    s_gt = torch.empty(S.shape[0], device=S.device, dtype=F32)
+    call("c2dsr_pick_target", ptr(S), S.stride(0), ptr(gt.contiguous(), I64), S.shape[0], n0, n1, ptr(s_gt), stream())
+    return s_gt
+
+
+def rank_from_scores(S, s_gt, gt, neg: Optional[torch.Tensor], n0: int, n1: int,
+                     counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """counts[i] += #{candidates j in [n0, n1), j != gt[i] : S[i, j - n0] > s_gt[i]} (int32)."""
+    n_q = S.shape[0]
+    if counts is None:
+        counts = torch.zeros(n_q, device=S.device, dtype=I32)
+    negc = None if neg is None else neg.contiguous()
+    call("c2dsr_rank_from_scores", ptr(S, F32), S.stride(0), ptr(s_gt, F32), ptr(gt.contiguous(), I64),
+         ptr(negc), 0 if negc is None else negc.shape[1], n_q, n0, n1, ptr(counts, I32), stream())
+    return counts

@@ -1,0 +1,201 @@
+"""``Trainer`` with the reference's interface (trainer.py:12-181): same constructor, attributes and
+method names / return types, so ``main.py`` drives it unchanged.  The step itself runs on the
+CUDA kernels behind the C ABI; torch supplies tensors, autograd bookkeeping and NCCL.
+
+Differences that are deliberate and visible:
+  * evaluation is batched (one device->host read per batch instead of one per sample) and can
+    rank against the full catalogue (``args.full_catalog``) instead of ``list_neg``;
+  * splits can live on the GPU (``args.data_on_device``, default on) so a batch is an index_select;
+  * with ``torch.distributed`` initialised, training is data-parallel and evaluation shards the
+    catalogue across ranks (dist.py).
+"""
+from __future__ import annotations
+
+import time
+from os.path import join
+
+import torch
+
+from . import dist as cdist
+from . import ops
+from .c2dsr import C2DSR
+from .dataloader import get_dataloader
+from .graph import make_graph
+from .optim import FusedAdamW
+
+
+class Trainer(object):
+    def __init__(self, args, noter):
+        self.rank, self.world_size = cdist.world()
+        args.rank, args.world_size = self.rank, self.world_size
+        self.trainloader, self.valloader, self.testloader = get_dataloader(args)
+        self.adj_share, self.adj_specific = make_graph(args, join(args.path_raw, 'train_new.txt'))
+        self._setup(args, noter)
+
+    @classmethod
+    def from_parts(cls, args, noter, loaders, adj_share, adj_specific):
+        """Build from already-made loaders and adjacencies (synthetic benchmarks, tests)."""
+        self = cls.__new__(cls)
+        self.rank, self.world_size = cdist.world()
+        self.trainloader, self.valloader, self.testloader = loaders
+        self.adj_share, self.adj_specific = adj_share, adj_specific
+        self._setup(args, noter)
+        return self
+
+    def _setup(self, args, noter):
+        self.args = args
+        self.device = torch.device(args.device)
+        self.model = C2DSR(args, self.adj_share, self.adj_specific).to(self.device)
+        self.optimizer = FusedAdamW(filter(lambda x: x.requires_grad, self.model.parameters()), lr=args.lr,
+                                    weight_decay=args.l2, amsgrad=True)
+        self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=args.lr_step, gamma=args.lr_gamma)
+        self.noter = noter
+        if getattr(args, "data_on_device", True):
+            for ld in (self.trainloader, self.valloader, self.testloader):
+                if ld is not None and hasattr(ld.dataset, "to"):
+                    ld.dataset.to(self.device)
+        self.n_tr = len(self.trainloader.dataset) if self.trainloader is not None else 0
+        self.n_val = len(self.valloader.dataset) if self.valloader is not None else 0
+        self.n_te = len(self.testloader.dataset) if self.testloader is not None else 0
+        self.d_latent = args.d_latent
+        self.n_item_a, self.n_item_b = args.n_item_a, args.n_item_b
+        self.len_rec = args.len_rec
+        self.lambda_loss = args.lambda_loss
+        self.full_catalog = bool(getattr(args, "full_catalog", False))
+        self.bucket = cdist.GradBucket()
+
+    # ------------------------------------------------------------------------------------------
+    def run_epoch(self):
+        """trainer.py:40-71 -> (ranks_a, ranks_b) of the validation split."""
+        self.model.train()
+        self.optimizer.zero_grad()                      # once per epoch: gradients accumulate (Q2)
+        sums = torch.zeros(3, device=self.device)
+        t_start = time.time()
+        for batch in self.trainloader:
+            self.model.convolve_graph()
+            losses = self.train_batch(batch)
+            sums += torch.stack(losses).detach() * (batch[0].shape[0] * self.world_size)
+        loss_tr, loss_rec, loss_mi = (sums / max(self.n_tr, 1)).tolist()    # one host sync per epoch
+        self.noter.log_train(loss_tr, loss_rec, loss_mi, time.time() - t_start)
+
+        self.model.eval()
+        pred_a, pred_b = [], []
+        with torch.no_grad():
+            self.model.convolve_graph()
+            for batch in self.valloader:
+                ra, rb = self.evaluate_batch(batch)
+                pred_a += ra
+                pred_b += rb
+        return pred_a, pred_b
+
+    def run_test(self):
+        """trainer.py:73-83; reuses the propagated tables of the validation pass (Q13)."""
+        self.model.eval()
+        pred_a, pred_b = [], []
+        with torch.no_grad():
+            for batch in self.testloader:
+                ra, rb = self.evaluate_batch(batch)
+                pred_a += ra
+                pred_b += rb
+        return pred_a, pred_b
+
+    def cal_mask(self, gt_mask):
+        """trainer.py:85-89 (kept for API parity; the infomax kernel computes the weights itself)."""
+        m = gt_mask.float()
+        return (m / m.sum(-1, keepdim=True)).unsqueeze(-1).repeat(1, 1, self.d_latent)
+
+    # ------------------------------------------------------------------------------------------
+    def losses(self, batch):
+        """Forward part of trainer.py:91-154 -> (loss, loss_rec, loss_mi), differentiable."""
+        (seq_share, seq_a, seq_b, pos, pos_a, pos_b, gt_share_a, gt_share_b, gt_a, gt_b, gt_mask_a, gt_mask_b,
+         seq_neg_a, seq_neg_b) = (x.to(self.device, non_blocking=True) for x in batch)
+        m = self.model
+        B, R, d = seq_share.shape[0], self.len_rec, self.d_latent
+        h_share, hx, hy, h_neg_a, h_neg_b = m.forward_all(seq_share, seq_a, seq_b, pos, pos_a, pos_b, seq_neg_a,
+                                                          seq_neg_b)
+        # normalisers are global-batch quantities under data parallelism
+        g_a, g_b = gt_a[:, -R:].reshape(-1), gt_b[:, -R:].reshape(-1)
+        counts = torch.stack(((g_a != self.n_item_a).sum(), (g_b != self.n_item_b).sum(),
+                              torch.tensor(B, device=self.device))).float()
+        cdist.allreduce_sum_(counts)
+        n_a, n_b, b_glob = counts[0], counts[1], counts[2]
+
+        loss_mi = ops.InfomaxFn.apply(h_share, hx, hy, h_neg_a, h_neg_b, m.D_a.weight, m.D_b.weight, m.D_a.bias,
+                                      m.D_b.bias, gt_mask_a, gt_mask_b, 1.0 / (B * self.world_size))
+
+        hs = h_share[:, -R:].reshape(-1, d)
+        ha, hb = hx[:, -R:].reshape(-1, d), hy[:, -R:].reshape(-1, d)
+        share_w = (1.0 / (R * b_glob)).expand(B * R)
+        parts = []
+        for h_dom, cls, g_share, g_dom, n_dom in ((ha, m.classifier_a, gt_share_a, g_a, n_a),
+                                                  (hb, m.classifier_b, gt_share_b, g_b, n_b)):
+            H = torch.cat((hs, hs + h_dom), 0)                 # item logits: h_share | h_share + h_dom
+            Hpad = torch.cat((hs, h_dom), 0)                   # pad logit:   h_share | h_dom      (Q5)
+            gt = torch.cat((g_share[:, -R:].reshape(-1), g_dom), 0)
+            w = torch.cat((share_w, (1.0 / n_dom).expand(B * R)), 0)   # loss_share re-weighting (Q11)
+            parts.append(ops.ScoreCEFn.apply(H, Hpad, cls.weight, cls.bias, m.classifier_pad.weight,
+                                             m.classifier_pad.bias, gt, w))
+        loss_rec = parts[0] + parts[1]
+        loss = self.lambda_loss * loss_rec + (1 - self.lambda_loss) * loss_mi
+        return loss, loss_rec, loss_mi
+
+    def train_batch(self, batch):
+        """trainer.py:91-160 -> (loss, loss_rec, loss_mi) as 0-d tensors (global values under DP)."""
+        loss, loss_rec, loss_mi = self.losses(batch)
+        loss.backward()
+        if self.world_size > 1:
+            self.optimizer.step(grads=self.bucket.reduce(self.optimizer.param_groups[0]["params"]))
+            out = torch.stack((loss.detach(), loss_rec.detach(), loss_mi.detach()))
+            cdist.allreduce_sum_(out)
+            return out[0], out[1], out[2]
+        self.optimizer.step()
+        return loss.detach(), loss_rec.detach(), loss_mi.detach()
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def eval_queries(self, batch):
+        """q_i = h_share[i, L-1] + (hx[i, idx_last_a] | hy[i, idx_last_b])  (trainer.py:169-177, Q8)."""
+        seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b, xory, gt_last, list_neg = batch
+        h_share, hx, hy = self.model(seq_share, seq_a, seq_b, pos, pos_a, pos_b)
+        B, L, _ = h_share.shape
+        ar = torch.arange(B, device=h_share.device)
+        dom_b = xory.view(-1) != 0
+        pick = torch.where(dom_b.unsqueeze(-1), hy[ar, idx_b.view(-1) % L], hx[ar, idx_a.view(-1) % L])
+        return h_share[:, -1] + pick, dom_b
+
+    @torch.no_grad()
+    def rank_queries(self, q, gt, neg, weight, bias):
+        """rank = 1 + #{candidates : s > s_gt}; catalogue rows sharded across ranks when distributed."""
+        n = weight.shape[0]
+        n0, n1 = cdist.shard_bounds(n, self.rank, self.world_size)
+        counts = torch.zeros(q.shape[0], dtype=torch.int32, device=q.device)
+        s_gt = torch.zeros(q.shape[0], dtype=torch.float32, device=q.device)
+        S = None
+        if n1 > n0 and q.shape[0] > 0:
+            S = ops.score_shard(q, weight[n0:n1], bias[n0:n1])
+            s_gt = ops.pick_target(S, gt, n0, n1)
+        cdist.allreduce_sum_(s_gt)
+        if S is not None:
+            ops.rank_from_scores(S, s_gt, gt, neg, n0, n1, counts)
+        cdist.allreduce_sum_(counts)
+        return counts + 1
+
+    @torch.no_grad()
+    def evaluate_batch(self, batch):
+        """trainer.py:162-181 -> (rank_a, rank_b) Python lists in batch order."""
+        xory_host = batch[8].view(-1).cpu() if not batch[8].is_cuda else None
+        batch = tuple(x.to(self.device, non_blocking=True) for x in batch)
+        gt_last, list_neg = batch[9].view(-1), batch[10]
+        q, dom_b = self.eval_queries(batch)
+        dom_b_host = (xory_host != 0) if xory_host is not None else dom_b.cpu()
+        out = []
+        for is_b, cls in ((False, self.model.classifier_a), (True, self.model.classifier_b)):
+            sel = torch.nonzero(dom_b_host == is_b).view(-1).to(self.device)
+            if sel.numel() == 0:
+                out.append([])
+                continue
+            neg = None if self.full_catalog else list_neg.index_select(0, sel)
+            ranks = self.rank_queries(q.index_select(0, sel).contiguous(), gt_last.index_select(0, sel), neg,
+                                      cls.weight, cls.bias)
+            out.append(ranks)
+        return tuple(r.tolist() if isinstance(r, torch.Tensor) else r for r in out)

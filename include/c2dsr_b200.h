@@ -1,0 +1,204 @@
+/* c2dsr_b200 -- C ABI of the B200-native C2DSR hot path (libc2dsr_b200.so, sm_100a only).
+ *
+ * The reference (crystal22/C2DSR) is pure PyTorch and has no FFI; its "operator interface" for
+ * this path is the set of torch calls listed below.  Each entry point names the reference call
+ * it replaces (file:line in the upstream repo).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
+ *     buffers, including scratch (sizes from the *_workspace_bytes functions);
+ *   - `stream` is a cudaStream_t passed as void*; no entry point synchronises, allocates or
+ *     keeps global mutable state, so all of them may be captured in a CUDA graph;
+ *   - return value 0 = OK, negative = error (-(cudaError_t) or a C2DSR_ERR_* code);
+ *     c2dsr_last_error() gives a thread-local message;
+ *   - matrices are row-major fp32, indices int64 (the reference uses LongTensor), CSR arrays int32;
+ *   - dropout: `p` drop probability, `seed`/`tag` select a counter-based mask that the matching
+ *     backward call regenerates from the same (seed, tag); p = 0 disables it;
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x every compute
+ *     entry returns C2DSR_ERR_ARCH.
+ */
+#ifndef C2DSR_B200_H
+#define C2DSR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2DSR_ABI_VERSION 1
+
+int c2dsr_abi_version(void);
+const char* c2dsr_last_error(void);
+/* 0 when the current device is a Blackwell sm_100 part, else C2DSR_ERR_ARCH. */
+int c2dsr_device_check(void);
+
+/* ---- K1: branch input = embedding gather --------------------------------------------------
+ * x[t,:] = drop( scale * (hi[seq[t],:] + E[seq[t],:]) + P[pos[t],:] )
+ * replaces F.embedding(seq, hi) + embed_i(seq), "*= sqrt(d)" (models/C2DSR.py:65-71,81-82) and
+ * "seq_enc += pos_emb(pos); dropout" (models/encoders.py:30-31). */
+int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int64_t* seq, const int64_t* pos,
+                     float* x, int64_t n_tok, int d, float scale, float p, uint64_t seed, uint64_t tag,
+                     void* stream);
+/* Backward of the above, deterministic (sort + segmented sum, no float atomics):
+ *   g[t] = dx[t] * mask;  d_P[pos[t]] += g[t];  S[n] = scale * sum_{t: seq[t]=n} g[t];
+ *   d_hi[n] += S[n];  d_E[n] += S[n] for n != pad_idx  (nn.Embedding padding_idx, C2DSR.py:20).
+ * replaces embedding_dense_backward reached from loss.backward() (trainer.py:156). */
+int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d);
+int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, float* d_hi, float* d_E, float* d_P,
+                     int64_t n_tok, int d, int64_t pad_idx, float scale, float p, uint64_t seed, uint64_t tag,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- K2: CSR SpMM for GCN propagation -----------------------------------------------------
+ * drop_mode 0: out = alpha * A X + beta * Y + gamma * Z
+ * drop_mode 1: out = alpha * A (m .* X) + ...      (mask indexed by the gathered row: forward)
+ * drop_mode 2: out = alpha * m .* (A X) + ...      (mask indexed by the output row: backward, A = A^T)
+ * Y, Z may be NULL; out may alias Y or Z.  replaces torch.spmm(adj, h) + stack/mean
+ * (models/encoders.py:43-48) and its autograd transpose product. */
+int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const float* X, const float* Y,
+               const float* Z, float* out, int64_t n_rows, int d, float alpha, float beta, float gamma,
+               int drop_mode, float p, uint64_t seed, uint64_t tag, void* stream);
+
+/* ---- dense building blocks ----------------------------------------------------------------
+ * C[M,N] = drop(act( alpha * op(A) op(B) + bias[N] )) + beta * C
+ *   ta = 0: A is [M,K] (lda)   ta = 1: A is stored [K,M] (lda)
+ *   tb = 0: B is [K,N] (ldb)   tb = 1: B is stored [N,K] (ldb)  -- the nn.Linear weight layout
+ * act 0 = none, 1 = relu.  fp32 FFMA path (exact fp32 products); workspace enables split-K.
+ * replaces nn.Linear / torch.mm on the path (encoder projections, nn.Bilinear, classifiers). */
+int64_t c2dsr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int c2dsr_gemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
+               const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act,
+               float p, uint64_t seed, uint64_t tag, void* workspace, int64_t workspace_bytes, void* stream);
+/* out[N] (+)= sum over rows of X[M,N] (ldx), fixed summation order. */
+int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* stream);
+/* out[0] = sum_i w[i] * x[i] (w may be NULL), single fixed-order reduction. */
+int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stream);
+
+/* ---- K3: SASRec-style encoder -------------------------------------------------------------
+ * replaces SelfAttention.forward -> nn.TransformerEncoder (models/encoders.py:23-33):
+ * n_layers x { MHA with allow[i,j] = (j <= i) && (seq[j] == pad), out-proj, LayerNorm(eps),
+ * FFN d->d (ReLU) ->d, LayerNorm }, then a final LayerNorm.  norm_first selects the pre-norm
+ * layer.  Rows with no allowed key attend to nothing (output 0). */
+typedef struct {
+    const float *in_proj_w, *in_proj_b;   /* [3d,d], [3d] */
+    const float *out_proj_w, *out_proj_b; /* [d,d], [d]   */
+    const float *lin1_w, *lin1_b;         /* [d,d], [d]   */
+    const float *lin2_w, *lin2_b;         /* [d,d], [d]   */
+    const float *ln1_w, *ln1_b, *ln2_w, *ln2_b; /* [d] each */
+} c2dsr_layer_weights;
+typedef struct {
+    float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+} c2dsr_layer_grads;
+
+/* floats the forward saves for the backward (`saved`), and scratch bytes for either pass */
+int64_t c2dsr_encoder_saved_floats(int64_t n_tok, int d, int n_head, int n_layers);
+int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head);
+int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers_host, int n_layers, const float* lnf_w, const float* lnf_b,
+                      const float* x, const int64_t* seq, int64_t n_seq, int L, int d, int n_head, int64_t pad_idx,
+                      int norm_first, float eps, float p, uint64_t seed, uint64_t tag, float* out, float* saved,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+/* Gradients are ACCUMULATED (+=) into `grads` and lnf grads; dx is overwritten. */
+int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers_host, const c2dsr_layer_grads* grads_host, int n_layers,
+                      const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,
+                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, float eps, float p,
+                      uint64_t seed, uint64_t tag, const float* saved, float* dx, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
+/* primitives of the encoder, exported for unit tests */
+int c2dsr_attention_fwd(const float* qkv, const int64_t* seq, int64_t n_seq, int L, int d, int n_head,
+                        int64_t pad_idx, float p, uint64_t seed, uint64_t tag, float* o, float* lse, void* stream);
+int c2dsr_attention_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
+                        int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, float p, uint64_t seed,
+                        uint64_t tag, float* d_qkv, void* stream);
+/* s = x + drop(y) (y may be NULL);  out = do_ln ? LayerNorm(s) * w + b : s;  stats[t] = (mean, rstd) */
+int c2dsr_add_ln_fwd(const float* x, const float* y, const float* w, const float* b, float* s_out, float* out,
+                     float* stats, int64_t n_tok, int d, int do_ln, float eps, float p, uint64_t seed, uint64_t tag,
+                     void* stream);
+/* ds = LayerNorm backward of d_out at (s, stats, w);  dx_out = (accumulate ? dx_out : 0) + ds */
+int c2dsr_ln_bwd(const float* d_out, const float* s, const float* stats, const float* w, float* dx_out,
+                 int accumulate, int64_t n_tok, int d, void* stream);
+/* d_w[d] += sum_t d_out * xhat,  d_b[d] += sum_t d_out */
+int c2dsr_ln_param_grad(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
+                        int64_t n_tok, int d, void* stream);
+
+/* ---- K5: infomax discriminator ------------------------------------------------------------
+ * replaces Trainer.cal_mask + masked pooling + nn.Bilinear + BCE-with-logits x4
+ * (trainer.py:85-119, models/C2DSR.py:46-55), including the crossed masks.
+ * pooled[6][B][d] = {x_mean, y_mean, share.wb, share.wa, neg_a.wa, neg_b.wb};
+ * loss[0] = sum of the four batch-mean BCE terms (batch mean over inv_batch = 1/B_global). */
+int64_t c2dsr_infomax_workspace_bytes(int64_t B, int d);
+int c2dsr_infomax_fwd(const float* h_share, const float* hx, const float* hy, const float* h_neg_a,
+                      const float* h_neg_b, const int64_t* gt_mask_a, const int64_t* gt_mask_b, const float* W_a,
+                      const float* W_b, const float* bias_a, const float* bias_b, int64_t B, int L, int d,
+                      float inv_batch, float* pooled, float* U, float* sims, float* loss, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+/* upstream: d_loss (device scalar).  d_h_* are ACCUMULATED (+=); dW/dbias accumulated. */
+int c2dsr_infomax_bwd(const float* d_loss, const float* pooled, const float* U, const float* sims,
+                      const int64_t* gt_mask_a, const int64_t* gt_mask_b, const float* W_a, const float* W_b,
+                      int64_t B, int L, int d, float inv_batch, float* d_h_share, float* d_hx, float* d_hy,
+                      float* d_h_neg_a, float* d_h_neg_b, float* dW_a, float* dW_b, float* dbias_a, float* dbias_b,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- K4a: classifier logits + cross-entropy (training) ------------------------------------
+ * For M rows H[M,d] against one domain's classifier W[N,d], b[N] plus the pad logit zpad[M]:
+ *   lse[m] = logsumexp([H W^T + b | zpad]);  loss_row[m] = gt[m] == N ? 0 : lse[m] - z[m, gt[m]]
+ * replaces classifier_x(h) + cat(classifier_pad) + F.cross_entropy(ignore_index=N)
+ * (trainer.py:131-152).  Z[M, ldz] (ldz = c2dsr_score_ldz(N)) is scratch kept for the backward. */
+int64_t c2dsr_score_ldz(int64_t N);
+int c2dsr_score_ce_fwd(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
+                       int64_t M, int64_t N, int d, float* Z, float* lse, float* loss_row, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* coef[m] = upstream * row weight.  Overwrites Z with dZ, then
+ * dH[M,d] = dZ W;  dW[N,d] += dZ^T H;  dbias[N] += colsum(dZ);  dzpad[m] = (exp(zpad-lse)) * coef. */
+int c2dsr_score_ce_bwd(const float* H, const float* W, const float* zpad, const int64_t* gt, const float* lse,
+                       const float* coef, int64_t M, int64_t N, int d, float* Z, float* dH, float* dW,
+                       float* dbias, float* dzpad, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- K4b: full-catalogue scoring + rank count (evaluation) ---------------------------------
+ * replaces the per-sample loop of Trainer.evaluate_batch (trainer.py:168-179):
+ *   s = W q + b;  rank = 1 + #{ j in candidates : s_j > s_gt }   (strict '>', fp32)
+ * Catalogue shard = items [n0, n1) of the domain (W, bias point at the shard's first row).
+ * Step 1 (scores):  S[Q, lds] = q W_shard^T + b_shard              -> c2dsr_score_shard
+ * Step 2 (target):  s_gt[i] = S[i, gt[i]-n0] if gt[i] in shard else 0 (sum across shards)
+ * Step 3 (count):   counts[i] += #{ j in shard, j != gt[i], (neg == NULL or j in neg[i]) : S[i,j] > s_gt[i] }
+ * rank = 1 + sum over shards of counts (integer all-reduce). */
+int c2dsr_score_shard(const float* Q, const float* W, const float* bias, int64_t n_q, int64_t n_shard, int d,
+                      float* S, int64_t lds, void* workspace, int64_t workspace_bytes, void* stream);
+int c2dsr_pick_target(const float* S, int64_t lds, const int64_t* gt, int64_t n_q, int64_t n0, int64_t n1,
+                      float* s_gt, void* stream);
+/* bit-exact counting contract: integer result from given fp32 scores.  neg: [n_q, n_neg] domain-local
+ * ids or NULL (full-catalogue mode). */
+int c2dsr_rank_from_scores(const float* S, int64_t lds, const float* s_gt, const int64_t* gt, const int64_t* neg,
+                           int64_t n_neg, int64_t n_q, int64_t n0, int64_t n1, int32_t* counts, void* stream);
+/* Fused tensor-core path: tcgen05 GEMM (bf16x3 split, fp32 accumulate in TMEM) with the count
+ * done in the epilogue; the score matrix never reaches HBM.  Two launches: target scores, then
+ * the counting GEMM.  W_hi/W_lo, Q_hi/Q_lo are the bf16 split produced by c2dsr_split_bf16. */
+int c2dsr_split_bf16(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo,
+                     void* stream);
+int64_t c2dsr_score_tc_workspace_bytes(int64_t n_q, int64_t n_shard, int d);
+int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
+                          const float* bias, const int64_t* gt, int64_t n_q, int64_t n0, int64_t n1, int d,
+                          int passes, float* s_gt, void* workspace, int64_t workspace_bytes, void* stream);
+int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
+                         const float* bias, const float* s_gt, const int64_t* gt, int64_t n_q, int64_t n0,
+                         int64_t n1, int d, int passes, int32_t* counts, float* S_debug, int64_t lds,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- optimiser -----------------------------------------------------------------------------
+ * AdamW with amsgrad on an accumulated gradient (trainer.py:21-22,42,157-158):
+ *   acc += g (if g != NULL);  p *= 1 - lr*wd;  m,v,vmax updated from acc;  p -= lr/bc1 * m / (sqrt(vmax)/sqrt(bc2) + eps)
+ * One launch over a table of n tensors (device arrays of pointers / sizes). */
+typedef struct {
+    float* p; const float* g; float* acc; float* m; float* v; float* vmax; int64_t n;
+} c2dsr_adam_tensor;
+int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, int step, void* stream);
+
+/* elementwise glue: out = a*x + b*y (y may be NULL) */
+int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2DSR_B200_H */

@@ -1,0 +1,89 @@
+"""world_size = 2 checks of the multi-GPU host logic on CPU (gloo): catalogue sharding with
+partial rank counts, the data-parallel gradient bucket and the global loss normalisers.  The
+per-rank compute is done by the oracle here (there is no GPU); the exchange logic under test is
+the code the CUDA path uses (c2dsr_b200/dist.py)."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c2dsr_oracle as oracle
+    from c2dsr_b200 import dist as cdist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    assert cdist.init_from_env("gloo")[:2] == (rank, world)
+    assert cdist.world() == (rank, world)
+    ok = True
+
+    # --- catalogue-sharded ranking: identical on every rank, equal to the unsharded oracle ---
+    rng = np.random.default_rng(0)
+    n_q, N, d = 37, 1003, 16
+    Q = rng.standard_normal((n_q, d)).astype(np.float32)
+    W = rng.standard_normal((N, d)).astype(np.float32)
+    gt = rng.integers(0, N, n_q)
+    S_full = Q @ W.T
+    ref = oracle.rank_from_scores(S_full, gt, None)
+    n0, n1 = cdist.shard_bounds(N, rank, world)
+    S = S_full[:, n0:n1]
+    own = (gt >= n0) & (gt < n1)
+    s_gt = torch.from_numpy(np.where(own, S_full[np.arange(n_q), gt], 0).astype(np.float32))
+    cdist.allreduce_sum_(s_gt)
+    ok &= bool(np.array_equal(s_gt.numpy(), S_full[np.arange(n_q), gt]))
+    col = np.arange(n0, n1)[None, :]
+    counts = torch.from_numpy(((S > s_gt.numpy()[:, None]) & (col != gt[:, None])).sum(1).astype(np.int32))
+    cdist.allreduce_sum_(counts)
+    ok &= bool(np.array_equal(counts.numpy() + 1, ref))
+
+    # --- gradient bucket: accumulated local grads -> accumulated global grads, dead params skipped ---
+    ps = [torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
+    ps[0].grad = torch.full((4, 3), float(rank + 1))
+    ps[1].grad = torch.arange(5.0) * (rank + 1)
+    bucket = cdist.GradBucket()
+    views = bucket.reduce(ps)
+    ok &= ps[2] not in views
+    ok &= bool(torch.equal(views[ps[0]], torch.full((4, 3), 3.0)))
+    ok &= bool(torch.equal(views[ps[1]], torch.arange(5.0) * 3))
+    ok &= bool(torch.equal(ps[0].grad, torch.full((4, 3), float(rank + 1))))     # local accumulators untouched
+    ps[0].grad += 1                                                               # next batch of the epoch
+    ok &= bool(torch.equal(bucket.reduce(ps)[ps[0]], torch.full((4, 3), 5.0)))
+
+    # --- global normalisers: sum of per-rank valid counts ---
+    c = torch.tensor([3.0 + rank, 7.0, 16.0])
+    cdist.allreduce_sum_(c)
+    ok &= c.tolist() == [7.0, 14.0, 32.0]
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_two_rank_exchange_logic():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_shard_bounds_partition():
+    from c2dsr_b200.dist import shard_bounds
+    for n in (1, 7, 29207, 1000001):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
+            assert all(hi >= lo for lo, hi in b)

@@ -1,0 +1,179 @@
+"""End-to-end parity on the B200 through the reference-shaped API (Trainer / C2DSR), against the
+golden vectors produced by the reference itself (tests/golden/make_golden.py) and against the CPU
+oracle at sizes it finishes in seconds.  Tolerances (north star): losses and scores 1e-4 relative,
+ranks exact given identical scores, Recall/MRR/NDCG within 1e-3 absolute."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_NAMES, Golden, rel_err
+import c2dsr_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class QuietNoter:
+    def log_train(self, *a):
+        pass
+
+    def log_msg(self, *a):
+        pass
+
+
+def _trainer_from_golden(g, state="init", **over):
+    from c2dsr_b200.dataloader import BatchLoader, CDSRDataset
+    from c2dsr_b200.trainer import Trainer
+    hp = dict(g.hp)
+    hp.update(over)
+    args = argparse.Namespace(**hp)
+    args.device = torch.device(DEV)
+    z = g.z
+    train = CDSRDataset.from_fields([z["train_fields"][:, i] for i in range(14)], "train", hp["len_max"])
+    evals = {}
+    for mode in ("val", "test"):
+        six, four, neg = z[f"{mode}_six"], z[f"{mode}_four"], z[f"{mode}_neg"]
+        evals[mode] = CDSRDataset.from_fields([six[:, i] for i in range(6)] + [four[:, i:i + 1] for i in range(4)]
+                                              + [neg], mode, hp["len_max"])
+    loaders = (BatchLoader(train, hp["batch_size"]), BatchLoader(evals["val"], hp["batch_size_eval"]),
+               BatchLoader(evals["test"], hp["batch_size_eval"]))
+    torch.manual_seed(hp["seed"])
+    tr = Trainer.from_parts(args, QuietNoter(), loaders, g.adj("share"), g.adj("spec"))
+    tr.model.load_state_dict({k: v.to(DEV) for k, v in g.group(state).items()})
+    return tr
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_training_steps_match_reference(name):
+    g = Golden(name)
+    tr = _trainer_from_golden(g)
+    tr.model.train()                                   # dropouts are 0 in the fixtures
+    tr.optimizer.zero_grad()
+    ref_losses = g.z["losses"]
+    for s in range(len(ref_losses)):
+        tr.model.convolve_graph()
+        if s == 0:
+            with torch.no_grad():
+                b = tuple(x.to(DEV) for x in g.train_batch(0))
+                hs, hx, hy = tr.model(*b[:6])
+                for got, key in ((hs, "h_share"), (hx, "hx"), (hy, "hy")):
+                    assert rel_err(got.cpu(), g.z["step0/" + key]) < 1e-4, key
+                assert rel_err(tr.model.hi_share.cpu(), g.z["step0/hi_share"]) < 1e-5
+                assert rel_err(tr.model.forward_share(b[12], b[3]).cpu(), g.z["step0/h_neg_a"]) < 1e-4
+        out = tr.train_batch(g.train_batch(s))
+        np.testing.assert_allclose([float(x) for x in out], ref_losses[s], rtol=1e-4)
+        if s == 0:
+            grads = g.group("grad0")
+            named = dict(tr.model.named_parameters())
+            for k, ref in grads.items():
+                assert named[k].grad is not None, k
+                if "in_proj" in k:                     # q/k rows: rounding noise only (see test_oracle_golden)
+                    d = g.hp["d_latent"]
+                    assert rel_err(named[k].grad[2 * d:].cpu(), ref[2 * d:]) < 1e-3, k
+                    continue
+                assert rel_err(named[k].grad.cpu(), ref) < 1e-3, k
+            assert all(p.grad is None for k, p in named.items() if ".encoder_layer." in k)   # Q3
+    final = g.group("final")
+    d, lr, n = g.hp["d_latent"], g.hp["lr"], len(ref_losses)
+    for k, p in tr.model.state_dict().items():
+        if k.endswith("attn_mask"):
+            continue
+        ref, got = final[k], p.cpu()
+        if "in_proj" in k:
+            assert rel_err(got[2 * d:], ref[2 * d:]) < 1e-3, k
+            assert float((got[:2 * d] - ref[:2 * d]).abs().max()) <= 2 * n * lr, k
+            continue
+        assert rel_err(got, ref) < 1e-3, k
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_eval_ranks_and_metrics_match_reference(name):
+    from c2dsr_b200.metrics import cal_score
+    g = Golden(name)
+    tr = _trainer_from_golden(g, state="final")
+    tr.model.eval()
+    with torch.no_grad():
+        tr.model.convolve_graph()
+        batch = g.eval_batch("val")
+        ra, rb = tr.evaluate_batch(batch)
+        hs, hx, hy = tr.model(*(x.to(DEV) for x in batch[:6]))
+    for got, key in ((hs, "h_share"), (hx, "hx"), (hy, "hy")):
+        assert rel_err(got.cpu(), g.z["eval/" + key]) < 1e-4, key
+    ref_a, ref_b = g.z["eval/rank_a"].tolist(), g.z["eval/rank_b"].tolist()
+    assert len(ra) == len(ref_a) and len(rb) == len(ref_b)
+    # identical up to comparisons the reference itself decides by < 1e-6 score margins
+    assert sum(abs(x - y) for x, y in zip(ra + rb, ref_a + ref_b)) <= 1
+    got = cal_score(ra, rb, [0.1124, 0.0865, 0.0574, 0.0416])
+    assert np.abs(np.asarray(got[1:]) - g.z["eval/score"][1:]).max() <= 1e-3 + 1.0 / min(len(ra), len(rb))
+    # full-catalogue mode against the oracle on the same weights
+    tr.full_catalog = True
+    fa, fb = tr.evaluate_batch(batch)
+    otr = oracle.OracleTrainer(g.group("final"), g.adj("share"), g.adj("spec"), g.hp)
+    otr.convolve_graph()
+    oa, ob = otr.evaluate_batch(batch, full_catalog=True)
+    assert sum(abs(x - y) for x, y in zip(fa + fb, oa + ob)) <= 1
+    assert all(f >= r for f, r in zip(fa + fb, ra + rb))           # more candidates can only push the rank up
+
+
+def test_run_epoch_and_run_test_contract():
+    """Trainer.run_epoch / run_test return two python lists of int ranks (trainer.py:40-83)."""
+    g = Golden("tiny_default")
+    tr = _trainer_from_golden(g, dropout_gnn=0.2, dropout_attn=0.2)       # reference default dropouts
+    va, vb = tr.run_epoch()
+    ta, tb = tr.run_test()
+    assert len(va) + len(vb) == len(g.z["val_four"]) and len(ta) + len(tb) == len(g.z["test_four"])
+    assert all(isinstance(r, int) and 1 <= r <= g.hp["n_neg_sample"] + 1 for r in va + vb + ta + tb)
+    # training moved the weights and the loss is finite
+    assert not torch.equal(tr.model.classifier_a.weight.cpu(), g.group("init")["classifier_a.weight"])
+    assert all(torch.isfinite(p).all() for p in tr.model.parameters())
+
+
+def test_training_with_dropout_learns():
+    """Dropout path sanity at the reference's default rates: loss decreases over a few epochs."""
+    g = Golden("tiny_default")
+    tr = _trainer_from_golden(g, dropout_gnn=0.2, dropout_attn=0.2, lr=5e-3)
+    tr.model.train()
+    first = last = None
+    for epoch in range(6):
+        tr.optimizer.zero_grad()
+        tot = 0.0
+        for batch in tr.trainloader:
+            tr.model.convolve_graph()
+            tot += float(tr.train_batch(batch)[0])
+        first = tot if first is None else first
+        last = tot
+    assert last < first
+
+
+def test_full_size_food_kitchen_eval_properties():
+    """BASELINE config 2 size (29 207 + 34 886 items, d = 256, 2 048 queries): size-independent
+    properties of the full-catalogue ranking -- shard sums equal the unsharded counts, list-mode rank
+    <= full rank, permuting the catalogue leaves every rank unchanged."""
+    from c2dsr_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    n_q, N, d = 2048, 34886, 256
+    Q = torch.randn(n_q, d, generator=gen).to(DEV)
+    W = (torch.randn(N, d, generator=gen) * 0.01).to(DEV)
+    b = torch.zeros(N, device=DEV)
+    gt = torch.randint(0, N, (n_q,), generator=gen).to(DEV)
+    S = ops.score_shard(Q, W, b)
+    s_gt = ops.pick_target(S, gt, 0, N)
+    full = ops.rank_from_scores(S, s_gt, gt, None, 0, N)
+    ref = (S[:, :N] > s_gt[:, None]).sum(1).to(torch.int32)
+    assert torch.equal(full, ref)
+    neg = torch.randint(0, N - 1, (n_q, 999), generator=gen).to(DEV)
+    neg = neg + (neg >= gt[:, None]).long()
+    assert bool((ops.rank_from_scores(S, s_gt, gt, neg, 0, N) <= full).all())
+    perm = torch.randperm(N, generator=gen).to(DEV)
+    inv = torch.empty_like(perm); inv[perm] = torch.arange(N, device=DEV)
+    S2 = ops.score_shard(Q, W[perm].contiguous(), b)
+    gt2 = inv[gt]
+    assert torch.equal(ops.rank_from_scores(S2, ops.pick_target(S2, gt2, 0, N), gt2, None, 0, N), full)
+    counts = torch.zeros(n_q, dtype=torch.int32, device=DEV)
+    for r in range(8):                                                # 8 catalogue shards, as on 8 GPUs
+        n0, n1 = (N + 7) // 8 * r, min((N + 7) // 8 * (r + 1), N)
+        Sr = ops.score_shard(Q, W[n0:n1], b[n0:n1])
+        ops.rank_from_scores(Sr, s_gt, gt, None, n0, n1, counts)
+    assert torch.equal(counts, full)
