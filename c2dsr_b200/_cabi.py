@@ -34,6 +34,7 @@ _PROTOS = {
     "c2dsr_abi_version": (i32, []),
     "c2dsr_last_error": (C.c_char_p, []),
     "c2dsr_device_check": (i32, []),
+    "c2dsr_launch_count": (i64, []),
     "c2dsr_gather_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32] + _DROP + [vp]),
     "c2dsr_gather_bwd_workspace_bytes": (i64, [i64, i32]),
     "c2dsr_gather_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, f32] + _DROP + [vp, i64, vp]),
@@ -118,12 +119,29 @@ def _require_device():
     _device_ok = True
 
 
+# Optional per-entry-point device timing (bench.py): PROFILE = {"names": set or None, "events": []}.
+# When set, matching calls are bracketed by CUDA events on the current stream.
+PROFILE = None
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point and raise on a non-zero status."""
     lib = _lib if (_lib is not None and _device_ok) else load()
-    rc = getattr(lib, name)(*args)
+    prof = PROFILE
+    if prof is not None and (prof["names"] is None or name in prof["names"]):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        prof["events"].append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise C2dsrError(f"{name} failed ({rc}): {lib.c2dsr_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load(check_device=False).c2dsr_launch_count())
 
 
 def query(name: str, *args) -> int:

@@ -13,7 +13,8 @@
 namespace c2dsr {
 
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);          // cudaGetLastError -> 0 / -(cudaError_t), records message
+int check_launch(const char* what);
+void note_launches(int n);                  // bookkeeping for c2dsr_launch_count()          // cudaGetLastError -> 0 / -(cudaError_t), records message
 
 #define C2DSR_REQUIRE(cond, msg)                                   \
     do {                                                           \

@@ -1,5 +1,6 @@
 // Error plumbing, device check, small elementwise / reduction kernels and the fused AdamW-amsgrad step.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 #include "common.cuh"
 #include "../../include/c2dsr_b200.h"
@@ -14,6 +15,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -99,6 +104,7 @@ using namespace c2dsr;
 extern "C" {
 
 int c2dsr_abi_version(void) { return C2DSR_ABI_VERSION; }
+int64_t c2dsr_launch_count(void) { return (int64_t)launches_so_far(); }
 const char* c2dsr_last_error(void) { return g_err; }
 
 int c2dsr_device_check(void) {
@@ -125,17 +131,20 @@ int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, 
     if (n <= 0) return C2DSR_OK;
     int blocks = (int)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
     axpby_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, out, n, a, b);
+    note_launches(1);
     return check_launch("axpby");
 }
 
 int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* stream) {
     if (N <= 0) return C2DSR_OK;
     colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out, accumulate);
+    note_launches(1);
     return check_launch("colsum");
 }
 
 int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stream) {
     wsum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, w, n, out);
+    note_launches(1);
     return check_launch("wsum");
 }
 
@@ -149,6 +158,7 @@ int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64
     if (chunks < 1) chunks = 1;
     adamw_kernel<<<dim3((unsigned)chunks, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(
         table_dev, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1), (float)sqrt(bc2));
+    note_launches(1);
     return check_launch("adamw_amsgrad");
 }
 

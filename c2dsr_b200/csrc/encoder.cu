@@ -329,16 +329,19 @@ static int launch_add_ln(const float* x, const float* y, const float* w, const f
                          float* stats, int64_t n_tok, int d, int do_ln, float eps, Dropout dr, cudaStream_t st) {
     add_ln_fwd_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(x, y, w, b, s_out, out, stats, n_tok, d, do_ln,
                                                                      eps, dr);
+    note_launches(1);
     return check_launch("add_ln_fwd");
 }
 static int launch_ln_bwd(const float* d_out, const float* s, const float* stats, const float* w, float* dx_out,
                          int accumulate, int64_t n_tok, int d, cudaStream_t st) {
     ln_bwd_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(d_out, s, stats, w, dx_out, accumulate, n_tok, d);
+    note_launches(1);
     return check_launch("ln_bwd");
 }
 static int launch_ln_param(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
                            int64_t n_tok, int d, cudaStream_t st) {
     ln_param_grad_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(d_out, s, stats, d_w, d_b, n_tok, d);
+    note_launches(1);
     return check_launch("ln_param_grad");
 }
 static AttnShape make_shape(int64_t n_seq, int L, int d, int H, int64_t pad) {
@@ -349,12 +352,14 @@ static int launch_attn_fwd(const float* qkv, const int64_t* seq, AttnShape sh, D
                            cudaStream_t st) {
     const int64_t warps = sh.n_seq * sh.H * sh.L;
     attn_fwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, seq, sh, dr, o, lse);
+    note_launches(1);
     return check_launch("attention_fwd");
 }
 static int launch_attn_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
                            AttnShape sh, Dropout dr, float* d_qkv, cudaStream_t st) {
     const int64_t warps = 2 * sh.n_seq * sh.H * sh.L;
     attn_bwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+    note_launches(1);
     return check_launch("attention_bwd");
 }
 static int launch_colsum_acc(const float* X, int64_t M, int64_t N, float* out, cudaStream_t st) {
@@ -554,6 +559,7 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         auto masked = [&](const float* src, uint64_t site) -> const float* {
             if (!has_drop) return src;
             drop_mul_kernel<<<ew_blocks(Td), 256, 0, st>>>(src, dy, Td, make_dropout(p, seed, tb + site));
+            note_launches(1);
             return dy;
         };
         // ---- feed-forward block ----
@@ -571,6 +577,7 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         RUN(launch_colsum_acc(d_y2, T, d, gw.lin2_b, st));
         RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y2, d, w.lin2_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         relu_drop_bwd_kernel<<<ew_blocks(Td), 256, 0, st>>>(dfd, s.fd, Td, inv_keep);
+        note_launches(1);
         RUN(gemm_dispatch(1, 0, d, d, T, 1.f, dfd, d, ffn_in, d, 1.f, gw.lin1_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_colsum_acc(dfd, T, d, gw.lin1_b, st));
         // gradient w.r.t. x1 (post-norm: d_s2 + d_pre W1; pre-norm: g + LN2^T(d_pre W1))

@@ -223,6 +223,7 @@ static int segmented_rowsum(const float* rows, const int64_t* key, float* out1, 
     SegArgs a{rows, key, perm, out1, out2, skip2, head, tail, n, d, scale, dr};
     seg_chunk_kernel<<<(unsigned)ceil_div(n_chunks, 4), 128, 0, st>>>(a);
     seg_stitch_kernel<<<(unsigned)ceil_div(n_chunks, 4), 128, 0, st>>>(a, n_chunks);
+    note_launches(3);
     return check_launch("segmented_rowsum");
 }
 
@@ -239,6 +240,7 @@ int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int6
     C2DSR_REQUIRE(d > 0 && d % 4 == 0, "d must be a positive multiple of 4");
     gather_fwd_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, (cudaStream_t)stream>>>(
         hi, E, P, seq, pos, x, n_tok, d, scale, make_dropout(p, seed, tag));
+    note_launches(1);
     return check_launch("gather_fwd");
 }
 

@@ -214,6 +214,7 @@ int gemm_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, 
     dim3 grid((unsigned)ceil_div(N, bm), (unsigned)ceil_div(M, bm), (unsigned)splits);
     if (small) launch_tile<64, 64>(ta, tb, grid, st, M, N, K, A, lda, B, ldb, C, ldc, ep, kps, ws);
     else launch_tile<128, 128>(ta, tb, grid, st, M, N, K, A, lda, B, ldb, C, ldc, ep, kps, ws);
+    note_launches(splits > 1 ? 2 : 1);
     if (splits > 1) {
         int64_t blocks = ceil_div(M * N, 256);
         if (blocks > 148 * 8) blocks = 148 * 8;

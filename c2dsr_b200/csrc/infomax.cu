@@ -175,6 +175,7 @@ int c2dsr_infomax_fwd(const float* h_share, const float* hx, const float* hy, co
                       workspace, workspace_bytes, st));
     sims_kernel<<<(unsigned)ceil_div(4 * B, 8), 256, 0, st>>>(pooled, U, bias_a, bias_b, B, d, sims);
     bce_loss_kernel<<<1, 1024, 0, st>>>(sims, B, inv_batch, loss);
+    note_launches(3);
     return check_launch("infomax_fwd");
 }
 
@@ -206,6 +207,7 @@ int c2dsr_infomax_bwd(const float* d_loss, const float* pooled, const float* U, 
     UnpoolDst dst;
     dst.d_h[0] = d_h_share; dst.d_h[1] = d_hx; dst.d_h[2] = d_hy; dst.d_h[3] = d_h_neg_a; dst.d_h[4] = d_h_neg_b;
     unpool_kernel<<<(unsigned)(B * L), 128, 0, st>>>(dst, gt_mask_a, gt_mask_b, dpool, B, L, d);
+    note_launches((dbias_a || dbias_b) ? 3 : 2);
     return check_launch("infomax_bwd");
 }
 

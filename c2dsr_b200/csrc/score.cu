@@ -141,6 +141,7 @@ int c2dsr_score_ce_fwd(const float* H, const float* W, const float* bias, const 
     RUN(gemm_dispatch(0, 1, M, N, d, 1.f, H, d, W, d, 0.f, Z, ldz, bias, 0, make_dropout(0.f, 0, 0), workspace,
                       workspace_bytes, st));
     ce_row_kernel<<<(unsigned)M, 256, 0, st>>>(Z, ldz, zpad, gt, N, lse, loss_row);
+    note_launches(1);
     return check_launch("score_ce_fwd");
 }
 
@@ -152,6 +153,7 @@ int c2dsr_score_ce_bwd(const float* H, const float* W, const float* zpad, const 
     const int64_t ldz = c2dsr_score_ldz(N);
     const Dropout none = make_dropout(0.f, 0, 0);
     ce_grad_kernel<<<(unsigned)M, 256, 0, st>>>(Z, ldz, zpad, gt, lse, coef, N, dzpad);
+    note_launches(1);
     RUN(gemm_dispatch(0, 0, M, d, N, 1.f, Z, ldz, W, d, 0.f, dH, d, nullptr, 0, none, workspace, workspace_bytes, st));
     RUN(gemm_dispatch(1, 0, N, d, M, 1.f, Z, ldz, H, d, 1.f, dW, d, nullptr, 0, none, workspace, workspace_bytes, st));
     RUN(c2dsr_colsum(Z, ldz, M, N, dbias, 1, st));
@@ -170,6 +172,7 @@ int c2dsr_pick_target(const float* S, int64_t lds, const int64_t* gt, int64_t n_
                       float* s_gt, void* stream) {
     if (n_q <= 0) return C2DSR_OK;
     pick_target_kernel<<<(unsigned)ceil_div(n_q, 256), 256, 0, (cudaStream_t)stream>>>(S, lds, gt, n_q, n0, n1, s_gt);
+    note_launches(1);
     return check_launch("pick_target");
 }
 
@@ -177,6 +180,7 @@ int c2dsr_rank_from_scores(const float* S, int64_t lds, const float* s_gt, const
                            int64_t n_neg, int64_t n_q, int64_t n0, int64_t n1, int32_t* counts, void* stream) {
     if (n_q <= 0) return C2DSR_OK;
     rank_count_kernel<<<(unsigned)n_q, 256, 0, (cudaStream_t)stream>>>(S, lds, s_gt, gt, neg, n_neg, n0, n1, counts);
+    note_launches(1);
     return check_launch("rank_from_scores");
 }
 

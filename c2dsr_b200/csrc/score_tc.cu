@@ -39,6 +39,7 @@ int c2dsr_split_bf16(const float* X, int64_t rows, int d, int64_t ld_out, uint16
     int64_t blocks = ceil_div(rows * (int64_t)d, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(X, rows, d, ld_out, hi, lo);
+    note_launches(1);
     return check_launch("split_bf16");
 }
 

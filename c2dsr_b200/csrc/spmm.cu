@@ -105,5 +105,6 @@ extern "C" int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float
     else if (d <= 512) LAUNCH(4);
     else LAUNCH(8);
 #undef LAUNCH
+    note_launches(1);
     return check_launch("spmm");
 }

@@ -184,7 +184,9 @@ class Trainer(object):
     def evaluate_batch(self, batch):
         """trainer.py:162-181 -> (rank_a, rank_b) Python lists in batch order."""
         xory_host = batch[8].view(-1).cpu() if not batch[8].is_cuda else None
-        batch = tuple(x.to(self.device, non_blocking=True) for x in batch)
+        # full-catalogue mode never reads list_neg: leave it on the host
+        batch = tuple(x if (i == 10 and self.full_catalog) else x.to(self.device, non_blocking=True)
+                      for i, x in enumerate(batch))
         gt_last, list_neg = batch[9].view(-1), batch[10]
         q, dom_b = self.eval_queries(batch)
         dom_b_host = (xory_host != 0) if xory_host is not None else dom_b.cpu()

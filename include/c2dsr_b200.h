@@ -32,6 +32,8 @@ int c2dsr_abi_version(void);
 const char* c2dsr_last_error(void);
 /* 0 when the current device is a Blackwell sm_100 part, else C2DSR_ERR_ARCH. */
 int c2dsr_device_check(void);
+/* Number of CUDA kernels this library has launched in this process (for benchmark accounting). */
+int64_t c2dsr_launch_count(void);
 
 /* ---- K1: branch input = embedding gather --------------------------------------------------
  * x[t,:] = drop( scale * (hi[seq[t],:] + E[seq[t],:]) + P[pos[t],:] )

@@ -55,7 +55,7 @@ def test_gather_fwd_bwd(B, L, d, N):
     assert torch.equal(x.cpu(), x_ref.detach())                      # same fp32 op order: bit-exact
     x.backward(dx.to(DEV))
     for got, ref, nm in ((hi_g.grad, hi_c.grad, "d_hi"), (E_g.grad, E_c.grad, "d_E"), (P_g.grad, P_c.grad, "d_P")):
-        assert rel_err(got.cpu(), ref) < 2e-6, nm
+        assert rel_err(got.cpu(), ref) < 1e-5, nm      # the pad row sums thousands of rows: order-dependent ulps
     assert float(E_g.grad[pad].abs().max()) == 0.0 and float(hi_g.grad[pad].abs().max()) > 0
     # determinism: a second backward gives identical bits (no float atomics)
     g1 = hi_g.grad.clone()
@@ -251,9 +251,11 @@ def test_encoder_fwd_bwd_vs_oracle(B, L, d, H, n_layers, norm_first):
         assert float((got.grad.cpu() - ref_t.grad).abs().max()) <= 1e-4 * scale + 1e-6
 
 
-def test_encoder_dropout_gradient_is_consistent():
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_encoder_dropout_gradient_is_consistent(p):
     """With dropout on, fwd and bwd must use the same masks: compare the analytic directional
-    derivative with a central finite difference of the (deterministic, seeded) forward."""
+    derivative with a central finite difference of the (deterministic, seeded) forward.  p = 0
+    calibrates the finite-difference error of the same check."""
     ops, _ = _ops()
     g = torch.Generator().manual_seed(3)
     B, L, d, H, nl, pad = 16, 10, 64, 2, 2, 999
@@ -262,16 +264,18 @@ def test_encoder_dropout_gradient_is_consistent():
     wl = [t.to(DEV) for t in _weight_list(_encoder_weights(d, nl, g), nl)]
     c = torch.randn(B, L, d, generator=g).to(DEV)
     v = torch.randn(B, L, d, generator=g).to(DEV)
-    f = lambda xx: float((ops.EncoderFn.apply(xx, seq, H, pad, False, 0.3, 1234, 5, *wl).double() * c.double()).sum())
-    out = ops.EncoderFn.apply(x, seq, H, pad, False, 0.3, 1234, 5, *wl)
+    f = lambda xx: float((ops.EncoderFn.apply(xx, seq, H, pad, False, p, 1234, 5, *wl).double() * c.double()).sum())
+    out = ops.EncoderFn.apply(x, seq, H, pad, False, p, 1234, 5, *wl)
     (out * c).sum().backward()
     analytic = float((x.grad.double() * v.double()).sum())
-    eps = 1e-2
-    numeric = (f(x.detach() + eps * v) - f(x.detach() - eps * v)) / (2 * eps)
-    assert abs(analytic - numeric) <= 2e-2 * max(abs(numeric), 1.0)
-    # and dropout really is on
-    out0 = ops.EncoderFn.apply(x.detach(), seq, H, pad, False, 0.0, 1234, 5, *wl)
-    assert rel_err(out.detach().cpu(), out0.cpu()) > 1e-2
+    errs = []
+    for eps in (4e-3, 1e-3):
+        numeric = (f(x.detach() + eps * v) - f(x.detach() - eps * v)) / (2 * eps)
+        errs.append(abs(analytic - numeric) / max(abs(numeric), 1.0))
+    assert min(errs) <= 1e-2, (analytic, errs)
+    if p > 0:                                                        # and dropout really is on
+        out0 = ops.EncoderFn.apply(x.detach(), seq, H, pad, False, 0.0, 1234, 5, *wl)
+        assert rel_err(out.detach().cpu(), out0.cpu()) > 1e-2
 
 
 # ------------------------------------------------------------------------------------------------
