@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dropout", type=float, default=0.2)
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
+    ap.add_argument("--score-path", type=str, default="tc", choices=["tc", "ffma"])
+    ap.add_argument("--tc-passes", type=int, default=3, choices=[1, 3])
     return ap.parse_args()
 
 
@@ -59,7 +61,7 @@ def hyper(wl, dropout, device):
         dropout_attn=dropout, norm_first=False, lr=1e-3, l2=5e-4, lr_gamma=0.5, lr_step=10, len_max=sh["len_max"],
         lambda_loss=0.7, seed=3407, batch_size=wl["batch_size"], batch_size_eval=wl["batch_size_eval"],
         n_item_a=na, n_item_b=nb, n_item=na + nb + 1, idx_pad=na + nb, device=device, full_catalog=True,
-        data_on_device=False)
+        data_on_device=False, score_path="tc", tc_passes=3)
 
 
 def make_workload(hp, n_train_batches, n_eval_batches, seed=0):
@@ -204,6 +206,7 @@ def run_b200(a):
     dev = torch.device("cuda", local_rank)
     wl = WORKLOADS[a.workload]
     hp = hyper(wl, a.dropout, dev)
+    hp.score_path, hp.tc_passes = a.score_path, a.tc_passes
     B, Bq, L, d, R = hp.batch_size, hp.batch_size_eval, hp.len_max, hp.d_latent, hp.len_rec
     n_tb = min(a.steps + a.warmup, 24)
     adj, fields, ev = make_workload(hp, n_tb * world, a.eval_batches, seed=0)
@@ -257,7 +260,8 @@ def run_b200(a):
         ev_fn = lambda batches: (lambda i: tr.evaluate_batch(batches[i % len(batches)]))
         for i in range(2):
             ev_fn(dev_eb)(i)
-        ev_dom = {"c2dsr_score_shard", "c2dsr_rank_from_scores", "c2dsr_pick_target"}
+        ev_dom = {"c2dsr_score_shard", "c2dsr_rank_from_scores", "c2dsr_pick_target", "c2dsr_score_count_tc",
+                  "c2dsr_score_target_tc"}
         _cabi.PROFILE = {"names": ev_dom, "events": []}
         ms_ev = timed(ev_fn(dev_eb), n_ev, world)
         prof_ev, _cabi.PROFILE = _cabi.PROFILE, None
@@ -304,7 +308,7 @@ def run_b200(a):
                      "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["tensor"], 5), "traffic": None, "peak_source": pk["src"] + " sustained",
                      "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / (ms / a.steps), 4),
-                     "path": os.environ.get("C2DSR_SCORE_PATH", "default")},
+                     "path": "ffma fp32 (materialised logits)"},
         "eval": {"metric": "full_catalog_eval_queries_per_sec", "value": round(eval_value, 1), "unit": "queries/s",
                  "batch": Bq, "batches": n_ev, "ms_per_batch": round(ms_ev / n_ev, 4),
                  "e2e": {"value": round(eval_e2e, 1), "unit": "queries/s",
@@ -312,7 +316,8 @@ def run_b200(a):
                          "d2h_bytes_per_step": Bq * 4},
                  "roofline": {"kernel": "K4b score + rank count", "bound": "tensor", "achieved": round(ev_ach, 3),
                               "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": round(ev_ach / pk["tensor_burst"], 5),
-                              "ms_per_batch": round(ev_dom_ms, 4), "peak_source": pk["src"] + " burst"}},
+                              "ms_per_batch": round(ev_dom_ms, 4), "peak_source": pk["src"] + " burst",
+                              "path": ("tcgen05 bf16x%d, fused count" % a.tc_passes) if a.score_path == "tc" else "ffma fp32"}},
     }
     if breakdown:
         out["breakdown_ms_per_step"] = breakdown

@@ -1,0 +1,306 @@
+// tcgen05 / TMEM / TMA building blocks for the score GEMMs (sm_100a).
+//
+// C[M, N] = A[M, K] * B[N, K]^T with both operands K-major bf16, fp32 accumulation in tensor memory.
+// fp32 fidelity comes from a split: x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the kernel issues
+// hi*hi + hi*lo + lo*hi per 64-wide k-block (the lo*lo term is below 2^-16 relative), so one staged
+// k-block of {A_hi, A_lo, B_hi, B_lo} feeds three MMA groups ("passes" = 3).  passes = 1 uses hi only.
+//
+// Kernel anatomy (one CTA per SM, persistent over output tiles):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier expect_tx
+//   warp 1      MMA issuer     one lane issues tcgen05.mma (M = 128, N = BN, K = 16), commits to mbarriers
+//   warp 2      TMEM allocator 2 accumulator stages x BN columns
+//   warps 4..7  epilogue       tcgen05.ld 32 lanes x 32 columns at a time; the functor consumes rows
+// so the epilogue of tile i overlaps the MMAs of tile i+1 and the TMA loads of tile i+2.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace c2dsr {
+namespace tc {
+
+constexpr int BM = 128;        // rows of A per tile = TMEM lanes
+constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom
+constexpr int UMMA_K = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D tiled load: coordinates are (inner = k element, outer = row)
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
+// ---- tensor memory ----
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulation
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives lane (base lane + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzled operand tile (rows of 64 bf16): start address, SBO = 8 rows * 128 B,
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  The tile base must be 1024-B aligned.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                 // leading byte offset: unused for swizzled K-major (canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Maps {
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+struct Problem {
+    int64_t M, N;       // rows of A, rows of B
+    int K;              // shared inner extent (elements)
+    int passes;         // 3 = hi/lo split, 1 = hi only
+    int diag_only;      // 1: only tiles with m_blk == n_blk (target-score pass, BN == BM)
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int A_TILE = BM * BK * 2;           // 16 KB
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    static constexpr int BARRIER_OFF = STAGES * STAGE;
+    static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;   // barriers + tmem pointer + alignment slack
+};
+
+// Epilogue functor contract:
+//   void tile_begin(int64_t m_blk, int64_t n_blk);
+//   void chunk(int64_t row, int64_t col0, const float (&v)[32]);   // row = global A row, cols col0..col0+31 of B
+//   void tile_end(int64_t row);
+template <int BN, int STAGES, class Epilogue>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BARRIER_OFF);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m_blocks = (pb.M + BM - 1) / BM, n_blocks = (pb.N + BN - 1) / BN;
+    const int64_t n_tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks;
+    const int n_kb = (pb.K + BK - 1) / BK;
+    const bool split = pb.passes == 3;
+    const uint32_t stage_bytes = split ? L::STAGE : (L::A_TILE + L::B_TILE);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a_hi);
+        tma_prefetch_desc(&maps.b_hi);
+        if (split) {
+            tma_prefetch_desc(&maps.a_lo);
+            tma_prefetch_desc(&maps.b_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    auto tile_coords = [&](int64_t t, int64_t& m_blk, int64_t& n_blk) {
+        if (pb.diag_only) {
+            m_blk = n_blk = t;
+        } else {
+            m_blk = t / n_blocks;
+            n_blk = t % n_blocks;
+        }
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int64_t m_blk, n_blk;
+            tile_coords(t, m_blk, n_blk);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = smem + stage * L::STAGE;
+                mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                tma_load_2d(&maps.a_hi, &full[stage], st, kb * BK, (int)(m_blk * BM));
+                tma_load_2d(&maps.b_hi, &full[stage], st + 2 * L::A_TILE, kb * BK, (int)(n_blk * BN));
+                if (split) {
+                    tma_load_2d(&maps.a_lo, &full[stage], st + L::A_TILE, kb * BK, (int)(m_blk * BM));
+                    tma_load_2d(&maps.b_lo, &full[stage], st + 2 * L::A_TILE + L::B_TILE, kb * BK, (int)(n_blk * BN));
+                }
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer ----------------
+        constexpr uint32_t idesc = make_idesc_bf16(BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t st = smem_u32(smem + stage * L::STAGE);
+                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + L::A_TILE);
+                const uint64_t b_hi = make_smem_desc(st + 2 * L::A_TILE);
+                const uint64_t b_lo = make_smem_desc(st + 2 * L::A_TILE + L::B_TILE);
+                uint32_t accum = kb > 0 ? 1u : 0u;
+                if (split) {      // small cross terms first, then the leading product
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accum);
+                        accum = 1u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                }
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accum);
+                    accum = 1u;
+                }
+                umma_commit(&empty[stage]);          // smem stage is free once these MMAs retire
+                if (++stage == STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue ----------------
+        const int q = warp - 4;                      // TMEM lane quarter owned by this warp
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            int64_t m_blk, n_blk;
+            tile_coords(t, m_blk, n_blk);
+            const int64_t row = m_blk * BM + q * 32 + lane;
+            epi.tile_begin(m_blk, n_blk, row);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                epi.chunk(row, n_blk * BN + c * 32, v);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            epi.tile_end(row);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+}  // namespace tc
+}  // namespace c2dsr

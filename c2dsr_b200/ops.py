@@ -291,3 +291,51 @@ def rank_from_scores(S, s_gt, gt, neg: Optional[torch.Tensor], n0: int, n1: int,
     call("c2dsr_rank_from_scores", ptr(S, F32), S.stride(0), ptr(s_gt, F32), ptr(gt.contiguous(), I64),
          ptr(negc), 0 if negc is None else negc.shape[1], n_q, n0, n1, ptr(counts, I32), stream())
     return counts
+
+
+# ------------------------------------------------------------------------------------------------
+# K4b, tensor-core path (tcgen05): fused score GEMM + rank count
+# ------------------------------------------------------------------------------------------------
+BF16 = torch.bfloat16
+
+
+def split_bf16(X: torch.Tensor, want_lo: bool = True):
+    """x = hi + lo with hi = bf16(x), lo = bf16(x - hi): operands of the 3-pass (fp32-grade) MMA."""
+    X = _f(X)
+    rows, d = X.shape
+    hi = torch.empty(rows, d, device=X.device, dtype=BF16)
+    lo = torch.empty(rows, d, device=X.device, dtype=BF16) if want_lo else None
+    call("c2dsr_split_bf16", ptr(X), rows, d, d, ptr(hi), ptr(lo), stream())
+    return hi, lo
+
+
+def score_rank_tc(Q, W_split, bias, gt, n0: int, n1: int, passes: int = 3, neg=None, s_gt=None,
+                  counts=None, want_scores: bool = False, reduce_s_gt=None):
+    """Full-catalogue partial rank counts of queries Q against the catalogue shard [n0, n1).
+
+    W_split = split_bf16(W[n0:n1]) (cached by the caller while the weights do not change).
+    Returns (counts int32 [n_q], s_gt fp32 [n_q], scores or None).  `reduce_s_gt` is called on the
+    target scores between the two launches (the cross-shard sum under catalogue sharding)."""
+    if neg is not None:
+        raise ValueError("the fused tensor-core path ranks against the full catalogue; use rank_from_scores for lists")
+    W_hi, W_lo = W_split
+    Q_hi, Q_lo = split_bf16(Q, passes == 3)
+    n_q, d = Q.shape
+    n = n1 - n0
+    dev = Q.device
+    gt = gt.contiguous()
+    bias = _f(bias)
+    ws = workspace.get(query("c2dsr_score_tc_workspace_bytes", n_q, n, d), dev)
+    if s_gt is None:
+        s_gt = torch.zeros(n_q, device=dev, dtype=F32)
+        call("c2dsr_score_target_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(gt, I64), n_q, n0, n1,
+             d, passes, ptr(s_gt), ptr(ws), ws.numel(), stream())
+        if reduce_s_gt is not None:
+            reduce_s_gt(s_gt)
+    if counts is None:
+        counts = torch.zeros(n_q, device=dev, dtype=I32)
+    lds = (n + 3) // 4 * 4
+    S = torch.empty(n_q, lds, device=dev, dtype=F32) if want_scores else None
+    call("c2dsr_score_count_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(s_gt), ptr(gt, I64), n_q,
+         n0, n1, d, passes, ptr(counts, I32), ptr(S), lds, None, 0, stream())
+    return counts, s_gt, S

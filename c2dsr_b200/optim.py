@@ -25,10 +25,12 @@ class FusedAdamW(torch.optim.Optimizer):
         self._table_key = None
         self._table_dev = None
         self._table_host = None
+        self.n_steps = 0          # bumped on every step(): parameters are updated through raw pointers
 
     @torch.no_grad()
     def step(self, closure=None, grads: Optional[Dict[torch.nn.Parameter, torch.Tensor]] = None):
         loss = closure() if closure is not None else None
+        self.n_steps += 1
         for gi, group in enumerate(self.param_groups):
             live = []
             for p in group["params"]:

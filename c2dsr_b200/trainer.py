@@ -62,7 +62,22 @@ class Trainer(object):
         self.len_rec = args.len_rec
         self.lambda_loss = args.lambda_loss
         self.full_catalog = bool(getattr(args, "full_catalog", False))
+        # "tc": tcgen05 GEMMs with the bf16 hi/lo split (3 passes = fp32-grade, 1 = plain bf16);
+        # "ffma": fp32 CUDA-core GEMMs with materialised scores (the comparison path)
+        self.score_path = getattr(args, "score_path", "tc")
+        self.tc_passes = int(getattr(args, "tc_passes", 3))
+        self._wsplit = {}
         self.bucket = cdist.GradBucket()
+
+    def _split_cache(self, weight, n0, n1):
+        """bf16 (hi, lo) split of a classifier shard, refreshed whenever the weights change."""
+        key = (weight.data_ptr(), n0, n1)
+        ver = (weight._version, getattr(self.optimizer, "n_steps", 0))   # raw-pointer updates do not bump _version
+        hit = self._wsplit.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.split_bf16(weight.detach()[n0:n1], self.tc_passes == 3))
+            self._wsplit[key] = hit
+        return hit[1]
 
     # ------------------------------------------------------------------------------------------
     def run_epoch(self):
@@ -168,6 +183,13 @@ class Trainer(object):
         """rank = 1 + #{candidates : s > s_gt}; catalogue rows sharded across ranks when distributed."""
         n = weight.shape[0]
         n0, n1 = cdist.shard_bounds(n, self.rank, self.world_size)
+        if neg is None and self.score_path == "tc" and q.shape[0] > 0:
+            # full catalogue on tensor cores: fused GEMM + count, scores never reach HBM
+            w_split = self._split_cache(weight, n0, n1)
+            counts, _, _ = ops.score_rank_tc(q, w_split, bias[n0:n1], gt, n0, n1, passes=self.tc_passes,
+                                             reduce_s_gt=cdist.allreduce_sum_)
+            cdist.allreduce_sum_(counts)
+            return counts + 1
         counts = torch.zeros(q.shape[0], dtype=torch.int32, device=q.device)
         s_gt = torch.zeros(q.shape[0], dtype=torch.float32, device=q.device)
         S = None
