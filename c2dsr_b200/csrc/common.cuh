@@ -55,17 +55,32 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint64_t tag) {
     return d;
 }
 
-__device__ __forceinline__ uint32_t hash32(uint64_t key, uint64_t idx) {
-    uint64_t z = key + idx * 0x9E3779B97F4A7C15ull;
+// One 64-bit mix serves a PAIR of consecutive elements: element idx uses the high half of
+// mix(idx >> 1) when idx is even, the low half when odd.  All kernels use these two helpers, so the
+// mask of element idx is the same whether it is generated one element or four at a time.
+__device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t pair) {
+    uint64_t z = key + pair * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (uint32_t)((z ^ (z >> 31)) >> 32);
+    return z ^ (z >> 31);
 }
 
 // multiplicative mask value: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_scale(const Dropout& d, uint64_t idx) {
     if (d.p == 0.f) return 1.f;
-    return hash32(d.key, idx) >= d.thresh ? d.inv_keep : 0.f;
+    const uint64_t z = mix64(d.key, idx >> 1);
+    const uint32_t h = (idx & 1) ? (uint32_t)z : (uint32_t)(z >> 32);
+    return h >= d.thresh ? d.inv_keep : 0.f;
+}
+
+// four consecutive elements starting at a multiple of 4
+__device__ __forceinline__ void drop_scale4(const Dropout& d, uint64_t base, float4& v) {
+    if (d.p == 0.f) return;
+    const uint64_t z0 = mix64(d.key, base >> 1), z1 = mix64(d.key, (base >> 1) + 1);
+    v.x *= (uint32_t)(z0 >> 32) >= d.thresh ? d.inv_keep : 0.f;
+    v.y *= (uint32_t)z0 >= d.thresh ? d.inv_keep : 0.f;
+    v.z *= (uint32_t)(z1 >> 32) >= d.thresh ? d.inv_keep : 0.f;
+    v.w *= (uint32_t)z1 >= d.thresh ? d.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

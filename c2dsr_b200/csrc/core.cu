@@ -54,6 +54,54 @@ __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t 
     }
 }
 
+// Two-phase variant for tall matrices: grid (column blocks, row chunks of kColChunk) writes chunk
+// partials, a second kernel adds them in chunk order.  Same fixed order on every run.
+constexpr int kColChunk = 128;
+__global__ void colsum_partial_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int64_t N,
+                                      float* __restrict__ partial) {
+    __shared__ float part[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * kColChunk;
+    const int64_t r1 = r0 + kColChunk < M ? r0 + kColChunk : M;
+    float s = 0.f;
+    if (c < N) {
+#pragma unroll 4
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += X[r * ldx + c];
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+        partial[(int64_t)blockIdx.y * N + c] = t;
+    }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t n_chunks, int64_t N,
+                                    float* __restrict__ out, int accumulate) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int64_t k = 0; k < n_chunks; ++k) s += partial[k * N + c];
+    out[c] = accumulate ? out[c] + s : s;
+}
+
+int colsum_dispatch(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* ws,
+                    int64_t ws_bytes, cudaStream_t st) {
+    if (N <= 0) return C2DSR_OK;
+    const int64_t n_chunks = ceil_div(M, kColChunk);
+    if (ws && n_chunks > 1 && n_chunks * N * 4 <= ws_bytes) {
+        colsum_partial_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)n_chunks), dim3(32, 8), 0, st>>>(
+            X, ldx, M, N, (float*)ws);
+        colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)ws, n_chunks, N, out, accumulate);
+        note_launches(2);
+    } else {
+        colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, st>>>(X, ldx, M, N, out, accumulate);
+        note_launches(1);
+    }
+    return check_launch("colsum");
+}
+
 // Single-block fixed-order weighted sum.
 __global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict__ w, int64_t n,
                             float* __restrict__ out) {
@@ -135,11 +183,9 @@ int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, 
     return check_launch("axpby");
 }
 
-int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* stream) {
-    if (N <= 0) return C2DSR_OK;
-    colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(X, ldx, M, N, out, accumulate);
-    note_launches(1);
-    return check_launch("colsum");
+int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* workspace,
+                 int64_t workspace_bytes, void* stream) {
+    return colsum_dispatch(X, ldx, M, N, out, accumulate, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stream) {

@@ -16,6 +16,11 @@ int gemm_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, 
                   Dropout dr, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
 constexpr int kMaxPerLane = 16;   // features per lane: d (or head dim) <= 512
+constexpr int64_t kGemmWsBytes = 16ll << 20;   // split-K partials / column-reduction partials
+constexpr int kLnChunk = 128;
+
+int colsum_dispatch(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* ws,
+                    int64_t ws_bytes, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm family: one warp per token, lane l owns features l, l+32, ...
@@ -132,6 +137,49 @@ __global__ void ln_param_grad_kernel(const float* __restrict__ d_out, const floa
         d_w[f] += a;
         d_b[f] += c;
     }
+}
+
+// two-phase form of the above: grid (feature blocks, token chunks) -> partials [chunk][2][d], summed in chunk order
+__global__ void ln_param_partial_kernel(const float* __restrict__ d_out, const float* __restrict__ s,
+                                        const float* __restrict__ stats, float* __restrict__ part, int64_t n_tok,
+                                        int d) {
+    __shared__ float pw[8][33], pb[8][33];
+    const int f = blockIdx.x * 32 + threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.y * kLnChunk;
+    const int64_t t1 = t0 + kLnChunk < n_tok ? t0 + kLnChunk : n_tok;
+    float sw = 0.f, sb = 0.f;
+    if (f < d) {
+#pragma unroll 4
+        for (int64_t t = t0 + threadIdx.y; t < t1; t += 8) {
+            const float go = d_out[t * d + f];
+            sw += go * (s[t * d + f] - stats[2 * t]) * stats[2 * t + 1];
+            sb += go;
+        }
+    }
+    pw[threadIdx.y][threadIdx.x] = sw;
+    pb[threadIdx.y][threadIdx.x] = sb;
+    __syncthreads();
+    if (threadIdx.y == 0 && f < d) {
+        float a = 0.f, c = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a += pw[k][threadIdx.x];
+            c += pb[k][threadIdx.x];
+        }
+        part[((int64_t)blockIdx.y * 2) * d + f] = a;
+        part[((int64_t)blockIdx.y * 2 + 1) * d + f] = c;
+    }
+}
+__global__ void ln_param_final_kernel(const float* __restrict__ part, int64_t n_chunks, int d, float* d_w, float* d_b) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= d) return;
+    float a = 0.f, c = 0.f;
+    for (int64_t k = 0; k < n_chunks; ++k) {
+        a += part[(k * 2) * d + f];
+        c += part[(k * 2 + 1) * d + f];
+    }
+    d_w[f] += a;
+    d_b[f] += c;
 }
 
 // out = in * dropout mask (same index space as the forward site)
@@ -338,10 +386,19 @@ static int launch_ln_bwd(const float* d_out, const float* s, const float* stats,
     note_launches(1);
     return check_launch("ln_bwd");
 }
-static int launch_ln_param(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
+static int launch_ln_param(void* ws, const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
                            int64_t n_tok, int d, cudaStream_t st) {
-    ln_param_grad_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(d_out, s, stats, d_w, d_b, n_tok, d);
-    note_launches(1);
+    const int64_t n_chunks = ceil_div(n_tok, kLnChunk);
+    if (ws && n_chunks > 1 && 2 * n_chunks * d * 4 <= kGemmWsBytes) {
+        float* part = (float*)ws;
+        ln_param_partial_kernel<<<dim3((unsigned)ceil_div(d, 32), (unsigned)n_chunks), dim3(32, 8), 0, st>>>(
+            d_out, s, stats, part, n_tok, d);
+        ln_param_final_kernel<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(part, n_chunks, d, d_w, d_b);
+        note_launches(2);
+    } else {
+        ln_param_grad_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(d_out, s, stats, d_w, d_b, n_tok, d);
+        note_launches(1);
+    }
     return check_launch("ln_param_grad");
 }
 static AttnShape make_shape(int64_t n_seq, int L, int d, int H, int64_t pad) {
@@ -362,8 +419,8 @@ static int launch_attn_bwd(const float* qkv, const float* o, const float* lse, c
     note_launches(1);
     return check_launch("attention_bwd");
 }
-static int launch_colsum_acc(const float* X, int64_t M, int64_t N, float* out, cudaStream_t st) {
-    return c2dsr_colsum(X, N, M, N, out, 1, st);
+static int launch_colsum_acc(void* ws, const float* X, int64_t M, int64_t N, float* out, cudaStream_t st) {
+    return colsum_dispatch(X, N, M, N, out, 1, ws, kGemmWsBytes, st);
 }
 static unsigned ew_blocks(int64_t n) {
     int64_t b = ceil_div(n, 256);
@@ -390,7 +447,6 @@ static LayerSaved carve(float* base, int64_t T, int d, int H) {
     s.st2 = p; p += T * 2;
     return s;
 }
-constexpr int64_t kGemmWsBytes = 16ll << 20;
 
 }  // namespace c2dsr
 
@@ -423,7 +479,7 @@ int c2dsr_ln_bwd(const float* d_out, const float* s, const float* stats, const f
 int c2dsr_ln_param_grad(const float* d_out, const float* s, const float* stats, float* d_w, float* d_b,
                         int64_t n_tok, int d, void* stream) {
     if (n_tok <= 0) return C2DSR_OK;
-    return launch_ln_param(d_out, s, stats, d_w, d_b, n_tok, d, (cudaStream_t)stream);
+    return launch_ln_param(nullptr, d_out, s, stats, d_w, d_b, n_tok, d, (cudaStream_t)stream);
 }
 
 int c2dsr_attention_fwd(const float* qkv, const int64_t* seq, int64_t n_seq, int L, int d, int n_head,
@@ -548,7 +604,7 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
     const bool has_drop = p > 0.f && p < 1.f;
     const float inv_keep = has_drop ? 1.f / (1.f - p) : 1.f;
 
-    RUN(launch_ln_param(d_out, xlast, stf, d_lnf_w, d_lnf_b, T, d, st));
+    RUN(launch_ln_param(gws, d_out, xlast, stf, d_lnf_w, d_lnf_b, T, d, st));
     RUN(launch_ln_bwd(d_out, xlast, stf, lnf_w, g, 0, T, d, st));
 
     for (int l = n_layers - 1; l >= 0; --l) {
@@ -567,24 +623,24 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         if (norm_first) {
             d_s2 = g;               // x2 = x1 + drop(y2): the sum is the layer output
         } else {
-            RUN(launch_ln_param(g, s.s2, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
+            RUN(launch_ln_param(gws, g, s.s2, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
             RUN(launch_ln_bwd(g, s.s2, s.st2, w.ln2_w, ds, 0, T, d, st));
             d_s2 = ds;
         }
         const float* d_y2 = masked(d_s2, 3);
         const float* ffn_in = norm_first ? s.s2 : s.x1;
         RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y2, d, s.fd, d, 1.f, gw.lin2_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-        RUN(launch_colsum_acc(d_y2, T, d, gw.lin2_b, st));
+        RUN(launch_colsum_acc(gws, d_y2, T, d, gw.lin2_b, st));
         RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y2, d, w.lin2_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         relu_drop_bwd_kernel<<<ew_blocks(Td), 256, 0, st>>>(dfd, s.fd, Td, inv_keep);
         note_launches(1);
         RUN(gemm_dispatch(1, 0, d, d, T, 1.f, dfd, d, ffn_in, d, 1.f, gw.lin1_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-        RUN(launch_colsum_acc(dfd, T, d, gw.lin1_b, st));
+        RUN(launch_colsum_acc(gws, dfd, T, d, gw.lin1_b, st));
         // gradient w.r.t. x1 (post-norm: d_s2 + d_pre W1; pre-norm: g + LN2^T(d_pre W1))
         float* d_x1;
         if (norm_first) {
             RUN(gemm_dispatch(0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-            RUN(launch_ln_param(ds, s.x1, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
+            RUN(launch_ln_param(gws, ds, s.x1, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
             RUN(launch_ln_bwd(ds, s.x1, s.st2, w.ln2_w, g, 1, T, d, st));
             d_x1 = g;
         } else {
@@ -596,21 +652,21 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         if (norm_first) {
             d_s1 = d_x1;            // x1 = xin + drop(y)
         } else {
-            RUN(launch_ln_param(d_x1, s.s1, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
+            RUN(launch_ln_param(gws, d_x1, s.s1, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
             RUN(launch_ln_bwd(d_x1, s.s1, s.st1, w.ln1_w, g, 0, T, d, st));
             d_s1 = g;
         }
         const float* d_y = masked(d_s1, 1);
         const float* attn_in = norm_first ? s.s1 : s.xin;
         RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y, d, s.o, d, 1.f, gw.out_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-        RUN(launch_colsum_acc(d_y, T, d, gw.out_proj_b, st));
+        RUN(launch_colsum_acc(gws, d_y, T, d, gw.out_proj_b, st));
         RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y, d, w.out_proj_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_attn_bwd(s.qkv, s.o, s.lse, dfd, seq, sh, make_dropout(p, seed, tb + 0), dqkv, st));
         RUN(gemm_dispatch(1, 0, 3 * d, d, T, 1.f, dqkv, 3 * d, attn_in, d, 1.f, gw.in_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-        RUN(launch_colsum_acc(dqkv, T, 3 * d, gw.in_proj_b, st));
+        RUN(launch_colsum_acc(gws, dqkv, T, 3 * d, gw.in_proj_b, st));
         if (norm_first) {
             RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
-            RUN(launch_ln_param(ds, s.xin, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
+            RUN(launch_ln_param(gws, ds, s.xin, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
             RUN(launch_ln_bwd(ds, s.xin, s.st1, w.ln1_w, g, 1, T, d, st));
         } else {
             RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 1.f, g, d, nullptr, 0, none, gws, kGemmWsBytes, st));

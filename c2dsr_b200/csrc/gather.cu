@@ -1,19 +1,23 @@
 // K1: branch-input gather  x = drop(scale * (hi[seq] + E[seq]) + P[pos])  and its deterministic backward.
 //
-// Forward is one warp per token, float4 lanes across the feature dimension: each token reads two table
+// Forward: one warp per token, float4 lanes across the feature dimension: each token reads two table
 // rows and one positional row (3 * d * 4 B) and writes one row (d * 4 B), fully coalesced.
 //
-// Backward needs a scatter-add of token rows into table rows (the pad row collects roughly half of
-// all tokens).  To keep it deterministic there are no float atomics: tokens are ranked by (key, index)
-// -- a stable sort by counting -- and summed segment by segment in sorted order.  Sorted positions are
-// cut into fixed chunks of 32; a warp sums the runs inside its chunk, runs that cross a chunk boundary
-// go through a per-chunk head/tail partial and are stitched together, in chunk order, by one warp.
+// Backward is a scatter-add of token rows g[t] into table rows, made deterministic without sorting and
+// without float atomics:
+//   * item rows: integer atomics elect, per item, the first token that references it and count the
+//     references.  An item referenced once (the common case) is written by that token's warp.  An item
+//     referenced several times is summed by its first token's warp, which scans the token list and adds
+//     the matching rows in token order.
+//   * the pad row (about half of all tokens) and the positional rows (at most len_max of them, every token
+//     contributes to one) are dense reductions: tokens are cut into fixed chunks, each chunk accumulates
+//     its (len_max + 1) bins in shared memory in token order, and a second kernel adds the chunk partials
+//     in chunk order.
+// Every float sum therefore has a fixed order; the integer atomics are order independent.
 #include "common.cuh"
 #include "../../include/c2dsr_b200.h"
 
 namespace c2dsr {
-
-constexpr int kChunk = 32;
 
 __global__ void gather_fwd_kernel(const float* __restrict__ hi, const float* __restrict__ E,
                                   const float* __restrict__ P, const int64_t* __restrict__ seq,
@@ -36,195 +40,106 @@ __global__ void gather_fwd_kernel(const float* __restrict__ hi, const float* __r
         r.y = __fadd_rn(__fmul_rn(__fadd_rn(a.y, b.y), scale), c.y);
         r.z = __fadd_rn(__fmul_rn(__fadd_rn(a.z, b.z), scale), c.z);
         r.w = __fadd_rn(__fmul_rn(__fadd_rn(a.w, b.w), scale), c.w);
-        if (dr.p != 0.f) {
-            const uint64_t base = (uint64_t)t * d + 4 * v;
-            r.x *= drop_scale(dr, base);
-            r.y *= drop_scale(dr, base + 1);
-            r.z *= drop_scale(dr, base + 2);
-            r.w *= drop_scale(dr, base + 3);
-        }
+        if (dr.p != 0.f) drop_scale4(dr, (uint64_t)t * d + 4 * v, r);
         o4[v] = r;
     }
 }
 
-// rank[t] = #{u : (key[u], u) < (key[t], t)}  -- stable sort position by counting.
-__global__ void rank_kernel(const int64_t* __restrict__ key, int64_t n, int32_t* __restrict__ perm) {
-    __shared__ int64_t tile[1024];
+// ---- backward -----------------------------------------------------------------------------------
+constexpr int kTokChunk = 64;      // tokens per dense-bin chunk
+constexpr int kSlab = 128;         // features per dense-bin block
+
+__global__ void mark_kernel(const int64_t* __restrict__ seq, int64_t n_tok, int64_t pad, int32_t* __restrict__ first,
+                            int32_t* __restrict__ cnt) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t mine = t < n ? key[t] : 0;
-    int cnt = 0;
-    for (int64_t base = 0; base < n; base += 1024) {
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) tile[i] = base + i < n ? key[base + i] : INT64_MAX;
-        __syncthreads();
-        const int lim = (int)(n - base < 1024 ? n - base : 1024);
-        if (t < n) {
-#pragma unroll 8
-            for (int i = 0; i < lim; ++i) {
-                const int64_t k = tile[i];
-                cnt += (k < mine) || (k == mine && base + i < t);
-            }
-        }
-        __syncthreads();
-    }
-    if (t < n) perm[cnt] = (int32_t)t;     // perm[sorted position] = token
+    if (t >= n_tok) return;
+    const int64_t k = seq[t];
+    if (k == pad) return;
+    atomicMin(first + k, (int32_t)t);
+    atomicAdd(cnt + k, 1);
 }
 
-// Single-CTA bitonic sort of (key << 32 | token) for n <= 16384: perm[sorted position] = token.
-__global__ void bitonic_perm_kernel(const int64_t* __restrict__ key, int n, int n2, int32_t* __restrict__ perm) {
-    extern __shared__ unsigned long long skeys[];
-    for (int i = threadIdx.x; i < n2; i += blockDim.x)
-        skeys[i] = i < n ? (((unsigned long long)key[i] << 32) | (unsigned)i) : ~0ull;
-    __syncthreads();
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long x = skeys[i], y = skeys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        skeys[i] = y;
-                        skeys[ixj] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[i] = (int32_t)(skeys[i] & 0xffffffffull);
-}
-
-struct SegArgs {
-    const float* rows;      // [n, d] token rows
-    const int64_t* key;     // [n]
-    const int32_t* perm;    // [n] sorted position -> token
-    float* out1;            // [*, d] accumulated
-    float* out2;            // optional second destination (same values)
-    int64_t skip2;          // key that out2 ignores (padding_idx), or -1
-    float* head;            // [n_chunks, d] partial of the run touching the chunk start
-    float* tail;            // [n_chunks, d] partial of the run touching the chunk end
-    int64_t n;
-    int d;
-    float scale;
-    Dropout dr;
-};
-
-__device__ __forceinline__ void seg_flush(const SegArgs& a, int64_t key, const float (&acc)[16], int nper, int lane,
-                                          float* dst_partial) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int f = lane + 32 * k;
-        if (k < nper && f < a.d) {
-            if (dst_partial) {
-                dst_partial[f] = acc[k];
-            } else {
-                a.out1[key * a.d + f] += acc[k];
-                if (a.out2 && key != a.skip2) a.out2[key * a.d + f] += acc[k];
-            }
-        }
-    }
-}
-
-// One warp per chunk of 32 sorted positions.  Lane l owns features l, l+32, ... (d <= 32*16).
-__global__ void seg_chunk_kernel(SegArgs a) {
+// one warp per token; lane l owns features l, l+32, ... (d <= 512)
+__global__ void item_rows_kernel(const float* __restrict__ dx, const int64_t* __restrict__ seq, int64_t n_tok, int d,
+                                 int64_t pad, float scale, Dropout dr, const int32_t* __restrict__ first,
+                                 const int32_t* __restrict__ cnt, float* d_hi, float* d_E) {
     const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int64_t lo = c * kChunk;
-    if (lo >= a.n) return;                                  // warp-uniform
-    const int cnt = (int)(lo + kChunk < a.n ? kChunk : a.n - lo);
-    const int nper = (a.d + 31) >> 5;
-    // lane l holds sorted position lo + l: its token and key, broadcast by shuffle below
-    const int32_t my_tok = lane < cnt ? a.perm[lo + lane] : 0;
-    const int64_t my_key = lane < cnt ? a.key[my_tok] : -1;
-    const int64_t prev_key = lo > 0 ? a.key[a.perm[lo - 1]] : -2;
-    const int64_t next_key = lo + cnt < a.n ? a.key[a.perm[lo + cnt]] : -2;
+    const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= n_tok) return;
+    const int64_t key = seq[t];
+    if (key == pad || first[key] != (int32_t)t) return;           // warp-uniform
+    const int nper = (d + 31) >> 5;
     float acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.f;
-    int64_t run_key = __shfl_sync(0xffffffffu, my_key, 0);
-    bool run_from_prev = prev_key == run_key;
-    for (int r = 0; r < cnt; ++r) {
-        const int64_t tok = __shfl_sync(0xffffffffu, my_tok, r);
-        const int64_t k = __shfl_sync(0xffffffffu, my_key, r);
-        if (k != run_key) {                                 // warp-uniform branch
-            seg_flush(a, run_key, acc, nper, lane, run_from_prev ? a.head + c * a.d : nullptr);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) acc[q] = 0.f;
-            run_key = k;
-            run_from_prev = false;
-        }
-        const float* row = a.rows + tok * a.d;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int f = lane + 32 * q;
-            if (q < nper && f < a.d) acc[q] += a.scale * __ldg(row + f) * drop_scale(a.dr, (uint64_t)tok * a.d + f);
-        }
-    }
-    float* dst = nullptr;
-    if (run_from_prev) dst = a.head + c * a.d;              // also the whole-chunk case
-    else if (next_key == run_key) dst = a.tail + c * a.d;
-    seg_flush(a, run_key, acc, nper, lane, dst);
-}
-
-// One warp per chunk whose last run starts a chunk-crossing segment: add tail[c] + head[c+1] + ... in order.
-__global__ void seg_stitch_kernel(SegArgs a, int64_t n_chunks) {
-    const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= n_chunks) return;
-    const int64_t last = (c + 1) * kChunk - 1;
-    if (last + 1 >= a.n) return;                                   // nothing after this chunk
-    const int64_t key = a.key[a.perm[last]];
-    if (a.key[a.perm[last + 1]] != key) return;                    // the last run ends here
-    const int64_t lo = c * kChunk;
-    const bool whole = a.key[a.perm[lo]] == key;                   // chunk is a single run
-    if (whole && lo > 0 && a.key[a.perm[lo - 1]] == key) return;   // segment started earlier: not the owner
-    const int nper = (a.d + 31) >> 5;
-    float acc[16];
-    // a whole-chunk run that starts its segment is stored in tail (run_from_prev false, run_to_next true)
-    const float* first = a.tail + c * a.d;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int f = lane + 32 * k;
-        acc[k] = (k < nper && f < a.d) ? first[f] : 0.f;
-    }
-    for (int64_t cc = c + 1; cc < n_chunks; ++cc) {
-        const float* h = a.head + cc * a.d;
+    auto add_row = [&](int64_t tok) {
+        const float* row = dx + tok * d;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int f = lane + 32 * k;
-            if (k < nper && f < a.d) acc[k] += h[f];
+            if (k < nper && f < d) acc[k] += scale * __ldg(row + f) * drop_scale(dr, (uint64_t)tok * d + f);
         }
-        const int64_t cl = (cc + 1) * kChunk - 1;                  // does the segment continue past chunk cc?
-        if (cl + 1 >= a.n) break;
-        if (a.key[a.perm[cl]] != key || a.key[a.perm[cl + 1]] != key) break;
+    };
+    if (cnt[key] == 1) {
+        add_row(t);
+    } else {
+        for (int64_t base = t & ~(int64_t)31; base < n_tok; base += 32) {      // earlier tokens cannot match
+            const int64_t j = base + lane;
+            unsigned m = __ballot_sync(0xffffffffu, j < n_tok && j >= t && seq[j] == key);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                add_row(base + b);
+            }
+        }
     }
-    seg_flush(a, key, acc, nper, lane, nullptr);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int f = lane + 32 * k;
+        if (k < nper && f < d) {
+            d_hi[key * d + f] += acc[k];
+            if (d_E) d_E[key * d + f] += acc[k];
+        }
+    }
 }
 
-static int segmented_rowsum(const float* rows, const int64_t* key, float* out1, float* out2, int64_t skip2,
-                            int64_t n, int d, float scale, Dropout dr, char* ws, cudaStream_t st) {
-    int32_t* perm = reinterpret_cast<int32_t*>(ws);
-    const int64_t n_chunks = ceil_div(n, kChunk);
-    float* head = reinterpret_cast<float*>(ws + align_up(n * 4, 256));
-    float* tail = head + n_chunks * d;
-    if (n <= 16384) {
-        int n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        const int smem = n2 * 8;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(bitonic_perm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-            attr_set = true;
+// grid (chunks, feature slabs), block kSlab threads, dynamic smem (n_bins * kSlab floats).
+// bins 0 .. L-1: positional rows (unscaled g); bin L: the pad item row (scale * g).
+__global__ void bin_partial_kernel(const float* __restrict__ dx, const int64_t* __restrict__ seq,
+                                   const int64_t* __restrict__ pos, int64_t n_tok, int d, int L, int64_t pad,
+                                   float scale, Dropout dr, float* __restrict__ partial) {
+    extern __shared__ float bins[];
+    const int n_bins = L + 1;
+    const int f = blockIdx.y * kSlab + threadIdx.x;
+    for (int b = 0; b < n_bins; ++b) bins[b * kSlab + threadIdx.x] = 0.f;
+    const int64_t t0 = (int64_t)blockIdx.x * kTokChunk;
+    const int64_t t1 = t0 + kTokChunk < n_tok ? t0 + kTokChunk : n_tok;
+    if (f < d) {
+        for (int64_t t = t0; t < t1; ++t) {
+            const float g = __ldg(dx + t * d + f) * drop_scale(dr, (uint64_t)t * d + f);
+            const int64_t ps = pos[t];
+            if (ps >= 0 && ps < L) bins[ps * kSlab + threadIdx.x] += g;
+            if (seq[t] == pad) bins[L * kSlab + threadIdx.x] += scale * g;
         }
-        bitonic_perm_kernel<<<1, 1024, smem, st>>>(key, (int)n, n2, perm);
-    } else {
-        rank_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(key, n, perm);
+        float* out = partial + ((int64_t)blockIdx.x * n_bins) * d + f;
+        for (int b = 0; b < n_bins; ++b) out[(int64_t)b * d] = bins[b * kSlab + threadIdx.x];
     }
-    SegArgs a{rows, key, perm, out1, out2, skip2, head, tail, n, d, scale, dr};
-    seg_chunk_kernel<<<(unsigned)ceil_div(n_chunks, 4), 128, 0, st>>>(a);
-    seg_stitch_kernel<<<(unsigned)ceil_div(n_chunks, 4), 128, 0, st>>>(a, n_chunks);
-    note_launches(3);
-    return check_launch("segmented_rowsum");
+}
+
+// thread per (bin, feature): add the chunk partials in chunk order
+__global__ void bin_reduce_kernel(const float* __restrict__ partial, int64_t n_chunks, int d, int L, int64_t pad,
+                                  float* d_P, float* d_hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_bins = L + 1;
+    if (i >= (int64_t)n_bins * d) return;
+    const int b = (int)(i / d), f = (int)(i % d);
+    float s = 0.f;
+    for (int64_t c = 0; c < n_chunks; ++c) s += partial[(c * n_bins + b) * d + f];
+    if (b < L) {
+        if (d_P) d_P[(int64_t)b * d + f] += s;
+    } else {
+        d_hi[pad * d + f] += s;                   // the pad row gets no direct-embedding gradient (padding_idx)
+    }
 }
 
 }  // namespace c2dsr
@@ -244,26 +159,45 @@ int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int6
     return check_launch("gather_fwd");
 }
 
-int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d) {
+int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d, int64_t n_rows, int len_max) {
     if (n_tok <= 0) return 256;
-    return align_up(n_tok * 4, 256) + 2 * ceil_div(n_tok, kChunk) * (int64_t)d * 4 + 256;
+    return align_up(2 * n_rows * 4, 256) + ceil_div(n_tok, kTokChunk) * (int64_t)(len_max + 1) * d * 4 + 256;
 }
 
 int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, float* d_hi, float* d_E, float* d_P,
-                     int64_t n_tok, int d, int64_t pad_idx, float scale, float p, uint64_t seed, uint64_t tag,
-                     void* workspace, int64_t workspace_bytes, void* stream) {
+                     int64_t n_tok, int d, int64_t n_rows, int len_max, int64_t pad_idx, float scale, float p,
+                     uint64_t seed, uint64_t tag, void* workspace, int64_t workspace_bytes, void* stream) {
     if (n_tok <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(d > 0 && d <= 512, "d must be in (0, 512]");
-    if (workspace_bytes < c2dsr_gather_bwd_workspace_bytes(n_tok, d)) {
+    C2DSR_REQUIRE(n_tok < (1ll << 31) && n_rows > 0 && len_max > 0, "bad sizes");
+    const int smem = (len_max + 1) * kSlab * 4;
+    C2DSR_REQUIRE(smem <= 200 * 1024, "len_max too large for the dense-bin reduction (<= 399)");
+    if (workspace_bytes < c2dsr_gather_bwd_workspace_bytes(n_tok, d, n_rows, len_max)) {
         set_error("gather_bwd: workspace too small");
         return C2DSR_ERR_WORKSPACE;
     }
-    Dropout dr = make_dropout(p, seed, tag);
+    const Dropout dr = make_dropout(p, seed, tag);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = segmented_rowsum(dx, seq, d_hi, d_E, pad_idx, n_tok, d, scale, dr, (char*)workspace, st);
-    if (rc) return rc;
-    if (d_P) rc = segmented_rowsum(dx, pos, d_P, nullptr, -1, n_tok, d, 1.f, dr, (char*)workspace, st);
-    return rc;
+    int32_t* first = (int32_t*)workspace;
+    int32_t* cnt = first + n_rows;
+    float* partial = (float*)((char*)workspace + align_up(2 * n_rows * 4, 256));
+    cudaMemsetAsync(first, 0x7f, n_rows * 4, st);
+    cudaMemsetAsync(cnt, 0, n_rows * 4, st);
+    mark_kernel<<<(unsigned)ceil_div(n_tok, 256), 256, 0, st>>>(seq, n_tok, pad_idx, first, cnt);
+    item_rows_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(dx, seq, n_tok, d, pad_idx, scale, dr, first, cnt,
+                                                                  d_hi, d_E);
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(bin_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    const int64_t n_chunks = ceil_div(n_tok, kTokChunk);
+    bin_partial_kernel<<<dim3((unsigned)n_chunks, (unsigned)ceil_div(d, kSlab)), kSlab, smem, st>>>(
+        dx, seq, pos, n_tok, d, len_max, pad_idx, scale, dr, partial);
+    bin_reduce_kernel<<<(unsigned)ceil_div((int64_t)(len_max + 1) * d, 256), 256, 0, st>>>(partial, n_chunks, d,
+                                                                                          len_max, pad_idx, d_P, d_hi);
+    note_launches(4);
+    return check_launch("gather_bwd");
 }
 
 }  // extern "C"

@@ -156,7 +156,7 @@ int c2dsr_score_ce_bwd(const float* H, const float* W, const float* zpad, const 
     note_launches(1);
     RUN(gemm_dispatch(0, 0, M, d, N, 1.f, Z, ldz, W, d, 0.f, dH, d, nullptr, 0, none, workspace, workspace_bytes, st));
     RUN(gemm_dispatch(1, 0, N, d, M, 1.f, Z, ldz, H, d, 1.f, dW, d, nullptr, 0, none, workspace, workspace_bytes, st));
-    RUN(c2dsr_colsum(Z, ldz, M, N, dbias, 1, st));
+    RUN(c2dsr_colsum(Z, ldz, M, N, dbias, 1, workspace, workspace_bytes, st));
     return check_launch("score_ce_bwd");
 }
 

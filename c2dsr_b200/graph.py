@@ -100,10 +100,30 @@ class CsrGraph:
         device = device if device is not None else adj.device
         self.rowptr, self.col, self.val = self._csr(idx[0], idx[1], val, n, device)
         self.t_rowptr, self.t_col, self.t_val = self._csr(idx[1], idx[0], val, n, device)
+        self.long_rows = self._long(self.rowptr)
+        self.t_long_rows = self._long(self.t_rowptr)
+
+    LONG_ROW = 256          # = c2dsr_spmm_long_row_threshold(): rows above it get a whole CTA in the SpMM
+
+    @classmethod
+    def _long(cls, rowptr):
+        deg = (rowptr[1:] - rowptr[:-1])
+        rows = torch.nonzero(deg > cls.LONG_ROW).view(-1).to(torch.int32)
+        return rows.contiguous() if rows.numel() else None
+
+    @property
+    def fwd(self):
+        return self.rowptr, self.col, self.val, self.long_rows
+
+    @property
+    def bwd(self):
+        return self.t_rowptr, self.t_col, self.t_val, self.t_long_rows
 
     def to(self, device):
-        for name in ("rowptr", "col", "val", "t_rowptr", "t_col", "t_val"):
-            setattr(self, name, getattr(self, name).to(device))
+        for name in ("rowptr", "col", "val", "t_rowptr", "t_col", "t_val", "long_rows", "t_long_rows"):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.to(device))
         return self
 
     @staticmethod

@@ -24,12 +24,14 @@ def _f(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K2: GCN propagation (models/encoders.py:42-48)
 # ------------------------------------------------------------------------------------------------
-def spmm(rowptr, col, val, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_mode=0, p=0.0,
-         seed=0, tag=0):
+def spmm(csr, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_mode=0, p=0.0, seed=0, tag=0):
+    """csr = (rowptr, col, val, long_rows or None) as held by graph.CsrGraph (.fwd / .bwd)."""
+    rowptr, col, val, long_rows = csr
     n, d = X.shape
     out = torch.empty_like(X) if out is None else out
-    call("c2dsr_spmm", ptr(rowptr, I32), ptr(col, I32), ptr(val, F32), ptr(X, F32), ptr(Y), ptr(Z), ptr(out, F32),
-         n, d, alpha, beta, gamma, drop_mode, p, seed, tag, stream())
+    call("c2dsr_spmm", ptr(rowptr, I32), ptr(col, I32), ptr(val, F32), ptr(long_rows),
+         0 if long_rows is None else long_rows.numel(), ptr(X, F32), ptr(Y), ptr(Z), ptr(out, F32), n, d, alpha, beta,
+         gamma, drop_mode, p, seed, tag, stream())
     return out
 
 
@@ -48,8 +50,8 @@ class GCNFn(torch.autograd.Function):
         for j in range(1, n_gnn + 1):
             t = tag * 16 + j
             if j == n_gnn:
-                return spmm(g.rowptr, g.col, g.val, h, Y=acc, alpha=c, beta=c, drop_mode=1, p=p, seed=seed, tag=t)
-            h = spmm(g.rowptr, g.col, g.val, h, drop_mode=1, p=p, seed=seed, tag=t)
+                return spmm(g.fwd, h, Y=acc, alpha=c, beta=c, drop_mode=1, p=p, seed=seed, tag=t)
+            h = spmm(g.fwd, h, drop_mode=1, p=p, seed=seed, tag=t)
             nxt = torch.empty_like(h)
             call("c2dsr_axpby", ptr(h), ptr(acc), ptr(nxt), h.numel(), 1.0, 1.0, stream())
             acc = nxt
@@ -62,10 +64,10 @@ class GCNFn(torch.autograd.Function):
             return d_hi, None, None, None, None, None
         c = 1.0 / (k + 1)
         # g_{j-1} = c d_hi + m_j .* (A^T g_j), g_k = c d_hi
-        cur = spmm(g.t_rowptr, g.t_col, g.t_val, d_hi, Y=d_hi, alpha=c, beta=c, drop_mode=2, p=p, seed=seed,
+        cur = spmm(g.bwd, d_hi, Y=d_hi, alpha=c, beta=c, drop_mode=2, p=p, seed=seed,
                    tag=tag * 16 + k)
         for j in range(k - 1, 0, -1):
-            cur = spmm(g.t_rowptr, g.t_col, g.t_val, cur, Y=d_hi, alpha=1.0, beta=c, drop_mode=2, p=p, seed=seed,
+            cur = spmm(g.bwd, cur, Y=d_hi, alpha=1.0, beta=c, drop_mode=2, p=p, seed=seed,
                        tag=tag * 16 + j)
         return cur, None, None, None, None, None
 
@@ -97,10 +99,10 @@ class GatherFn(torch.autograd.Function):
         d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
         d_P = torch.zeros(p_shape, device=dx.device, dtype=F32)
         n = seq.numel()
-        nb = query("c2dsr_gather_bwd_workspace_bytes", n, d)
+        nb = query("c2dsr_gather_bwd_workspace_bytes", n, d, n_rows, p_shape[0])
         ws = workspace.get(nb, dx.device)
-        call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, pad_idx, scale,
-             p, seed, tag, ptr(ws), ws.numel(), stream())
+        call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, n_rows, p_shape[0],
+             pad_idx, scale, p, seed, tag, ptr(ws), ws.numel(), stream())
         return d_hi, d_E, d_P, None, None, None, None, None, None, None
 
 

@@ -28,8 +28,11 @@ SHAPES = {
 FK_LEN_HIST = {6: 1130, 7: 1215, 8: 1137, 9: 918, 10: 717, 11: 629, 12: 509, 13: 389, 14: 385, 15: 1144}
 
 
-def _zipf_sampler(n: int, alpha: float, rng: np.random.Generator):
-    p = np.arange(1, n + 1, dtype=np.float64) ** (-alpha)
+def _zipf_sampler(n: int, alpha: float, rng: np.random.Generator, offset: float = 50.0):
+    # Zipf-Mandelbrot: p(r) ~ (r + offset)^-alpha.  The offset flattens the head so that the most popular
+    # item is seen ~10^2 times at Food-Kitchen size, like the shipped val_new.txt (max out-degree ~10^2,
+    # SURVEY.md section 8(d)); a pure power law would give a 10x heavier head than the real logs.
+    p = (np.arange(1, n + 1, dtype=np.float64) + offset) ** (-alpha)
     cdf = np.cumsum(p / p.sum())
     perm = rng.permutation(n)                       # popularity is not correlated with the id
     return lambda size: perm[np.minimum(np.searchsorted(cdf, rng.random(size)), n - 1)]

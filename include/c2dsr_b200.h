@@ -42,24 +42,28 @@ int64_t c2dsr_launch_count(void);
 int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int64_t* seq, const int64_t* pos,
                      float* x, int64_t n_tok, int d, float scale, float p, uint64_t seed, uint64_t tag,
                      void* stream);
-/* Backward of the above, deterministic (sort + segmented sum, no float atomics):
+/* Backward of the above, deterministic (first-reference election with integer atomics + ordered sums,
+ * no float atomics; n_rows = rows of the item tables, len_max = rows of P):
  *   g[t] = dx[t] * mask;  d_P[pos[t]] += g[t];  S[n] = scale * sum_{t: seq[t]=n} g[t];
  *   d_hi[n] += S[n];  d_E[n] += S[n] for n != pad_idx  (nn.Embedding padding_idx, C2DSR.py:20).
  * replaces embedding_dense_backward reached from loss.backward() (trainer.py:156). */
-int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d);
+int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d, int64_t n_rows, int len_max);
 int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, float* d_hi, float* d_E, float* d_P,
-                     int64_t n_tok, int d, int64_t pad_idx, float scale, float p, uint64_t seed, uint64_t tag,
-                     void* workspace, int64_t workspace_bytes, void* stream);
+                     int64_t n_tok, int d, int64_t n_rows, int len_max, int64_t pad_idx, float scale, float p,
+                     uint64_t seed, uint64_t tag, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- K2: CSR SpMM for GCN propagation -----------------------------------------------------
  * drop_mode 0: out = alpha * A X + beta * Y + gamma * Z
  * drop_mode 1: out = alpha * A (m .* X) + ...      (mask indexed by the gathered row: forward)
  * drop_mode 2: out = alpha * m .* (A X) + ...      (mask indexed by the output row: backward, A = A^T)
- * Y, Z may be NULL; out may alias Y or Z.  replaces torch.spmm(adj, h) + stack/mean
+ * Y, Z may be NULL; out may alias Y or Z (not X).  long_rows (optional, device) lists the rows that are
+ * split across a CTA to bound the heavy tail.  replaces torch.spmm(adj, h) + stack/mean
  * (models/encoders.py:43-48) and its autograd transpose product. */
-int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const float* X, const float* Y,
-               const float* Z, float* out, int64_t n_rows, int d, float alpha, float beta, float gamma,
-               int drop_mode, float p, uint64_t seed, uint64_t tag, void* stream);
+int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* long_rows, int n_long,
+               const float* X, const float* Y, const float* Z, float* out, int64_t n_rows, int d, float alpha,
+               float beta, float gamma, int drop_mode, float p, uint64_t seed, uint64_t tag, void* stream);
+/* Rows with more non-zeros than this should be listed in long_rows (they get a whole CTA each). */
+int c2dsr_spmm_long_row_threshold(void);
 
 /* ---- dense building blocks ----------------------------------------------------------------
  * C[M,N] = drop(act( alpha * op(A) op(B) + bias[N] )) + beta * C
@@ -71,8 +75,10 @@ int64_t c2dsr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int c2dsr_gemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act,
                float p, uint64_t seed, uint64_t tag, void* workspace, int64_t workspace_bytes, void* stream);
-/* out[N] (+)= sum over rows of X[M,N] (ldx), fixed summation order. */
-int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* stream);
+/* out[N] (+)= sum over rows of X[M,N] (ldx), fixed summation order.  With a workspace of at least
+ * ceil(M/128) * N floats the reduction runs in two phases over a 2-D grid. */
+int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* workspace,
+                 int64_t workspace_bytes, void* stream);
 /* out[0] = sum_i w[i] * x[i] (w may be NULL), single fixed-order reduction. */
 int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stream);
 

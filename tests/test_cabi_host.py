@@ -46,7 +46,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_size_queries_need_no_device(built_lib):
     from c2dsr_b200 import _cabi
     assert _cabi.query("c2dsr_score_ldz", 29207) == 29208
-    assert _cabi.query("c2dsr_gather_bwd_workspace_bytes", 3840, 256) > 3840 * 4
+    assert _cabi.query("c2dsr_gather_bwd_workspace_bytes", 3840, 256, 64094, 15) > 2 * 64094 * 4
     assert _cabi.query("c2dsr_encoder_saved_floats", 3840, 256, 1, 1) == 3840 * (9 * 256 + 1 + 4) + 3840 * 258
 
 
