@@ -231,7 +231,7 @@ def run_b200(a):
     step = train_step(dev_tb)
     for i in range(a.warmup):
         step(i)
-    dom = {"c2dsr_score_ce_fwd", "c2dsr_score_ce_bwd"}
+    dom = {"c2dsr_score_ce_fwd", "c2dsr_score_ce_bwd", "c2dsr_score_ce_fwd_tc", "c2dsr_score_ce_bwd_tc"}
     _cabi.PROFILE = {"names": dom, "events": []}
     l0 = _cabi.launch_count()
     clk = ClockSampler(local_rank)
@@ -308,7 +308,8 @@ def run_b200(a):
                      "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["tensor"], 5), "traffic": None, "peak_source": pk["src"] + " sustained",
                      "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / (ms / a.steps), 4),
-                     "path": "ffma fp32 (materialised logits)"},
+                     "path": ("tcgen05 bf16x%d: fused log-sum-exp forward, recompute + 2 gradient GEMMs backward" % a.tc_passes)
+                     if a.score_path == "tc" else "ffma fp32 (materialised logits)"},
         "eval": {"metric": "full_catalog_eval_queries_per_sec", "value": round(eval_value, 1), "unit": "queries/s",
                  "batch": Bq, "batches": n_ev, "ms_per_batch": round(ms_ev / n_ev, 4),
                  "e2e": {"value": round(eval_e2e, 1), "unit": "queries/s",

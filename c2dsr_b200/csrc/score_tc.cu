@@ -3,19 +3,10 @@
 // and consumed in the epilogue (compare with the target score, count) -- the [n_q, N] score matrix
 // never reaches HBM.  The target score itself comes from the same MMA sequence applied to the gathered
 // target rows, so "s_j > s_gt" compares numbers produced by identical arithmetic.
-#include "common.cuh"
-#include "tc_gemm.cuh"
+#include "tc_host.cuh"
 #include "../../include/c2dsr_b200.h"
 
 namespace c2dsr {
-
-// fp32 -> (hi, lo) bf16 split: hi = bf16(x), lo = bf16(x - hi).
-__device__ __forceinline__ uint16_t f32_to_bf16_rn(float f) {
-    uint32_t u = __float_as_uint(f);
-    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);   // inf / nan
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
 
 __global__ void split_bf16_kernel(const float* __restrict__ X, int64_t rows, int d, int64_t ld_out,
                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
@@ -23,12 +14,53 @@ __global__ void split_bf16_kernel(const float* __restrict__ X, int64_t rows, int
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / d;
         const int c = (int)(i % d);
-        const float x = X[i];
-        const uint16_t h = f32_to_bf16_rn(x);
-        const float hf = __uint_as_float((uint32_t)h << 16);
+        uint16_t h, l;
+        split2(X[i], h, l);
         hi[r * ld_out + c] = h;
-        if (lo) lo[r * ld_out + c] = f32_to_bf16_rn(x - hf);
+        if (lo) lo[r * ld_out + c] = l;
     }
+}
+
+// 32 x 32 tiles through shared memory: coalesced reads of X rows, coalesced writes of XT rows
+__global__ void split_bf16_T_kernel(const float* __restrict__ X, int64_t rows, int d, int64_t ld_out,
+                                    uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int64_t r = r0 + j;
+        const int c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < d) ? X[r * d + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + threadIdx.x;
+        if (c < d && r < rows) {
+            uint16_t h, l;
+            split2(tile[threadIdx.x][j], h, l);
+            hi[(int64_t)c * ld_out + r] = h;
+            if (lo) lo[(int64_t)c * ld_out + r] = l;
+        }
+    }
+}
+
+int split_rows(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo, cudaStream_t st) {
+    if (rows <= 0) return C2DSR_OK;
+    int64_t blocks = ceil_div(rows * (int64_t)d, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, d, ld_out, hi, lo);
+    note_launches(1);
+    return check_launch("split_bf16");
+}
+
+int split_rows_transposed(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo,
+                          cudaStream_t st) {
+    if (rows <= 0) return C2DSR_OK;
+    split_bf16_T_kernel<<<dim3((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(d, 32)), dim3(32, 8), 0, st>>>(
+        X, rows, d, ld_out, hi, lo);
+    note_launches(1);
+    return check_launch("split_bf16_T");
 }
 
 // G[i, :] = W[gt[i] - n0, :] for targets inside the shard, zeros otherwise; bias_gt[i] likewise.
@@ -57,7 +89,7 @@ struct CountEpilogue {
     float tgt;
     int64_t g_local;
     int cnt;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row) {
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int) {
         cnt = 0;
         if (row < M) {
             tgt = s_gt[row];
@@ -85,7 +117,7 @@ struct DiagEpilogue {       // BN == BM: element (row, row) of tile (b, b)
     const float* bias_gt;    // [M]
     float* s_gt;             // [M]
     int64_t M;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t) {}
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int) {}
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M || row < col0 || row >= col0 + 32) return;
         const int want = (int)(row - col0);
@@ -98,77 +130,7 @@ struct DiagEpilogue {       // BN == BM: element (row, row) of tile (b, b)
     __device__ __forceinline__ void tile_end(int64_t) {}
 };
 
-// ---- host helpers --------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
-    return fn;
-}
-
-// bf16 matrix [rows, k] with leading dimension ld (elements): box = 64 (k) x box_rows, 128-byte swizzle
-int make_bf16_map(CUtensorMap* map, const void* base, int64_t rows, int64_t k, int64_t ld, int box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return C2DSR_ERR_ARCH;
-    }
-    if (((uintptr_t)base & 15) || (ld * 2) % 16) {
-        set_error("TMA operand must be 16-byte aligned with a leading dimension that is a multiple of 8");
-        return C2DSR_ERR_ARG;
-    }
-    cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)(rows > 0 ? rows : 1)};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-        return C2DSR_ERR_ARG;
-    }
-    return C2DSR_OK;
-}
-
-static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 constexpr int kBN = 128, kStages = 3;
-
-template <class Epi>
-static int launch_gemm(const tc::Maps& maps, const tc::Problem& pb, const Epi& epi, cudaStream_t st) {
-    using L = tc::SmemLayout<kBN, kStages>;
-    auto kern = tc::gemm_kernel<kBN, kStages, Epi>;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-        attr = true;
-    }
-    const int64_t m_blocks = ceil_div(pb.M, tc::BM), n_blocks = ceil_div(pb.N, kBN);
-    const int64_t tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks;
-    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, 256, L::TOTAL, st>>>(maps, pb, epi);
-    note_launches(1);
-    return check_launch("tc_gemm");
-}
 
 }  // namespace c2dsr
 
@@ -184,12 +146,7 @@ extern "C" {
 
 int c2dsr_split_bf16(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo,
                      void* stream) {
-    if (rows <= 0) return C2DSR_OK;
-    int64_t blocks = ceil_div(rows * (int64_t)d, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_bf16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(X, rows, d, ld_out, hi, lo);
-    note_launches(1);
-    return check_launch("split_bf16");
+    return split_rows(X, rows, d, ld_out, hi, lo, (cudaStream_t)stream);
 }
 
 int64_t c2dsr_score_tc_workspace_bytes(int64_t n_q, int64_t n_shard, int d) {
@@ -218,13 +175,11 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
                                                              d, G_hi, passes == 3 ? G_lo : nullptr, bias_gt);
     note_launches(1);
     tc::Maps maps;
-    RUN(make_bf16_map(&maps.a_hi, Q_hi, n_q, d, d, tc::BM));
-    RUN(make_bf16_map(&maps.b_hi, G_hi, n_q, d, d, kBN));
-    RUN(make_bf16_map(&maps.a_lo, passes == 3 ? Q_lo : Q_hi, n_q, d, d, tc::BM));
-    RUN(make_bf16_map(&maps.b_lo, passes == 3 ? G_lo : G_hi, n_q, d, d, kBN));
-    tc::Problem pb{n_q, n_q, d, passes, 1};
+    RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
+    tc::Problem pb{n_q, n_q, d, passes, 1, 1};
     DiagEpilogue epi{bias_gt, s_gt, n_q};
-    return launch_gemm(maps, pb, epi, st);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true>(maps, pb, epi, st);
+    return launch_gemm<kBN, kStages, false>(maps, pb, epi, st);
 }
 
 int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
@@ -238,13 +193,12 @@ int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint1
     C2DSR_REQUIRE(d % 8 == 0, "d must be a multiple of 8");
     const int64_t n = n1 - n0;
     tc::Maps maps;
-    RUN(make_bf16_map(&maps.a_hi, Q_hi, n_q, d, d, tc::BM));
-    RUN(make_bf16_map(&maps.b_hi, W_hi, n, d, d, kBN));
-    RUN(make_bf16_map(&maps.a_lo, passes == 3 ? Q_lo : Q_hi, n_q, d, d, tc::BM));
-    RUN(make_bf16_map(&maps.b_lo, passes == 3 ? W_lo : W_hi, n, d, d, kBN));
-    tc::Problem pb{n_q, n, d, passes, 0};
+    RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, W_hi, W_lo, n, d, d, passes));
+    tc::Problem pb{n_q, n, d, passes, 0, 1};
     CountEpilogue epi{bias, s_gt, gt, counts, S_debug, lds, n_q, n, n0, 0.f, 0, 0};
-    return launch_gemm(maps, pb, epi, (cudaStream_t)stream);
+    // the queries' row block stays resident in shared memory when it fits (d <= 256); same MMA sequence either way
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true>(maps, pb, epi, (cudaStream_t)stream);
+    return launch_gemm<kBN, kStages, false>(maps, pb, epi, (cudaStream_t)stream);
 }
 
 }  // extern "C"

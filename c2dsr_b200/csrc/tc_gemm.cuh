@@ -2,15 +2,22 @@
 //
 // C[M, N] = A[M, K] * B[N, K]^T with both operands K-major bf16, fp32 accumulation in tensor memory.
 // fp32 fidelity comes from a split: x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the kernel issues
-// hi*hi + hi*lo + lo*hi per 64-wide k-block (the lo*lo term is below 2^-16 relative), so one staged
+// lo*hi + hi*lo + hi*hi per 64-wide k-block (the lo*lo term is below 2^-16 relative), so one staged
 // k-block of {A_hi, A_lo, B_hi, B_lo} feeds three MMA groups ("passes" = 3).  passes = 1 uses hi only.
 //
-// Kernel anatomy (one CTA per SM, persistent over output tiles):
-//   warp 0      TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier expect_tx
+// Kernel anatomy (one CTA per SM, persistent over a contiguous range of output tiles):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem, mbarrier expect_tx
 //   warp 1      MMA issuer     one lane issues tcgen05.mma (M = 128, N = BN, K = 16), commits to mbarriers
 //   warp 2      TMEM allocator 2 accumulator stages x BN columns
 //   warps 4..7  epilogue       tcgen05.ld 32 lanes x 32 columns at a time; the functor consumes rows
 // so the epilogue of tile i overlaps the MMAs of tile i+1 and the TMA loads of tile i+2.
+//
+// Two operand-staging modes:
+//   ARES = false  every k-block stage holds A and B tiles (any K; used for the long-K gradient GEMMs,
+//                 optionally split along K into slabs whose partial sums the caller adds in order)
+//   ARES = true   the whole A row block (all k-blocks, hi and lo) stays resident in shared memory while
+//                 the CTA walks consecutive N tiles, so only B is streamed: half the L2->SM traffic of
+//                 the streaming mode.  Needs K <= 256 (the logits / score GEMMs with d <= 256).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -22,6 +29,7 @@ namespace tc {
 constexpr int BM = 128;        // rows of A per tile = TMEM lanes
 constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
+constexpr int ARES_MAX_KB = 4; // resident A: up to 4 k-blocks (K <= 256)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -47,7 +55,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -131,39 +138,50 @@ struct Problem {
     int K;              // shared inner extent (elements)
     int passes;         // 3 = hi/lo split, 1 = hi only
     int diag_only;      // 1: only tiles with m_blk == n_blk (target-score pass, BN == BM)
+    int k_splits;       // >= 1: K is cut into this many slabs; the epilogue receives the slab index
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool ARES>
 struct SmemLayout {
     static constexpr int A_TILE = BM * BK * 2;           // 16 KB
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    static constexpr int BARRIER_OFF = STAGES * STAGE;
+    static constexpr int A_RES = ARES ? ARES_MAX_KB * 2 * A_TILE : 0;     // resident A row block (hi, lo)
+    static constexpr int STAGE = (ARES ? 0 : 2 * A_TILE) + 2 * B_TILE;
+    static constexpr int B_OFF = ARES ? 0 : 2 * A_TILE;   // offset of B_hi inside a stage
+    static constexpr int RING_OFF = A_RES;
+    static constexpr int BARRIER_OFF = RING_OFF + STAGES * STAGE;
     static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;   // barriers + tmem pointer + alignment slack
 };
 
-// Epilogue functor contract:
-//   void tile_begin(int64_t m_blk, int64_t n_blk);
-//   void chunk(int64_t row, int64_t col0, const float (&v)[32]);   // row = global A row, cols col0..col0+31 of B
+// Epilogue functor contract (one instance per epilogue thread; the thread owns A row `row`):
+//   void tile_begin(int64_t m_blk, int64_t n_blk, int64_t row, int k_slab);
+//   void chunk(int64_t row, int64_t col0, const float (&v)[32]);   // columns col0..col0+31 of the tile
 //   void tile_end(int64_t row);
-template <int BN, int STAGES, class Epilogue>
+template <int BN, int STAGES, bool ARES, class Epilogue>
 __global__ void __launch_bounds__(256, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, ARES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem + L::RING_OFF;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BARRIER_OFF);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* a_full = tmem_empty + 2;
+    uint64_t* a_empty = a_full + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m_blocks = (pb.M + BM - 1) / BM, n_blocks = (pb.N + BN - 1) / BN;
-    const int64_t n_tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks;
-    const int n_kb = (pb.K + BK - 1) / BK;
+    const int ks = pb.k_splits > 1 ? pb.k_splits : 1;
+    const int64_t n_tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks * ks;
+    const int n_kb_total = (pb.K + BK - 1) / BK;
+    const int kb_per_slab = (n_kb_total + ks - 1) / ks;
     const bool split = pb.passes == 3;
-    const uint32_t stage_bytes = split ? L::STAGE : (L::A_TILE + L::B_TILE);
+    const uint32_t stage_bytes = (ARES ? 0u : (uint32_t)L::A_TILE * (split ? 2u : 1u)) + (uint32_t)L::B_TILE * (split ? 2u : 1u);
+    // contiguous tile range of this CTA (consecutive tiles share the A row block)
+    const int64_t t0 = n_tiles * blockIdx.x / gridDim.x, t1 = n_tiles * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a_hi);
@@ -182,6 +200,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], 4);
         }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
@@ -190,32 +210,53 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    auto tile_coords = [&](int64_t t, int64_t& m_blk, int64_t& n_blk) {
+    // tile t -> (m_blk, n_blk, k slab); slabs of one output tile are consecutive
+    auto tile_coords = [&](int64_t t, int64_t& m_blk, int64_t& n_blk, int& slab) {
         if (pb.diag_only) {
             m_blk = n_blk = t;
+            slab = 0;
         } else {
-            m_blk = t / n_blocks;
-            n_blk = t % n_blocks;
+            slab = (int)(t % ks);
+            const int64_t mn = t / ks;
+            m_blk = mn / n_blocks;
+            n_blk = mn % n_blocks;
         }
+    };
+    auto kb_range = [&](int slab, int& kb0, int& kb1) {
+        kb0 = slab * kb_per_slab;
+        kb1 = kb0 + kb_per_slab < n_kb_total ? kb0 + kb_per_slab : n_kb_total;
     };
 
     if (warp == 0 && lane == 0) {
         // ---------------- TMA producer ----------------
         int stage = 0;
-        uint32_t phase = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t phase = 0, a_phase = 0;
+        int64_t cur_m = -1;
+        for (int64_t t = t0; t < t1; ++t) {
             int64_t m_blk, n_blk;
-            tile_coords(t, m_blk, n_blk);
-            for (int kb = 0; kb < n_kb; ++kb) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                uint8_t* st = smem + stage * L::STAGE;
-                mbar_arrive_expect_tx(&full[stage], stage_bytes);
-                tma_load_2d(&maps.a_hi, &full[stage], st, kb * BK, (int)(m_blk * BM));
-                tma_load_2d(&maps.b_hi, &full[stage], st + 2 * L::A_TILE, kb * BK, (int)(n_blk * BN));
-                if (split) {
-                    tma_load_2d(&maps.a_lo, &full[stage], st + L::A_TILE, kb * BK, (int)(m_blk * BM));
-                    tma_load_2d(&maps.b_lo, &full[stage], st + 2 * L::A_TILE + L::B_TILE, kb * BK, (int)(n_blk * BN));
+            int slab, kb0, kb1;
+            tile_coords(t, m_blk, n_blk, slab);
+            kb_range(slab, kb0, kb1);
+            if (ARES && m_blk != cur_m) {
+                mbar_wait(a_empty, a_phase ^ 1);              // MMAs of the previous row block are done
+                mbar_arrive_expect_tx(a_full, (uint32_t)n_kb_total * (uint32_t)L::A_TILE * (split ? 2u : 1u));
+                for (int kb = 0; kb < n_kb_total; ++kb) {
+                    tma_load_2d(&maps.a_hi, a_full, smem + kb * 2 * L::A_TILE, kb * BK, (int)(m_blk * BM));
+                    if (split) tma_load_2d(&maps.a_lo, a_full, smem + kb * 2 * L::A_TILE + L::A_TILE, kb * BK, (int)(m_blk * BM));
                 }
+                a_phase ^= 1;
+                cur_m = m_blk;
+            }
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* st = ring + stage * L::STAGE;
+                mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                if (!ARES) {
+                    tma_load_2d(&maps.a_hi, &full[stage], st, kb * BK, (int)(m_blk * BM));
+                    if (split) tma_load_2d(&maps.a_lo, &full[stage], st + L::A_TILE, kb * BK, (int)(m_blk * BM));
+                }
+                tma_load_2d(&maps.b_hi, &full[stage], st + L::B_OFF, kb * BK, (int)(n_blk * BN));
+                if (split) tma_load_2d(&maps.b_lo, &full[stage], st + L::B_OFF + L::B_TILE, kb * BK, (int)(n_blk * BN));
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -226,19 +267,31 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = make_idesc_bf16(BN);
         int stage = 0, acc = 0;
-        uint32_t phase = 0, acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t phase = 0, acc_phase = 0, a_phase = 0;
+        int64_t cur_m = -1;
+        for (int64_t t = t0; t < t1; ++t) {
+            int64_t m_blk, n_blk;
+            int slab, kb0, kb1;
+            tile_coords(t, m_blk, n_blk, slab);
+            kb_range(slab, kb0, kb1);
+            if (ARES && m_blk != cur_m) {
+                if (cur_m >= 0) umma_commit(a_empty);          // previous row block no longer needed
+                mbar_wait(a_full, a_phase);
+                a_phase ^= 1;
+                cur_m = m_blk;
+            }
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < n_kb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t st = smem_u32(smem + stage * L::STAGE);
-                const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + L::A_TILE);
-                const uint64_t b_hi = make_smem_desc(st + 2 * L::A_TILE);
-                const uint64_t b_lo = make_smem_desc(st + 2 * L::A_TILE + L::B_TILE);
-                uint32_t accum = kb > 0 ? 1u : 0u;
+                const uint32_t st = smem_u32(ring + stage * L::STAGE);
+                const uint32_t a_base = ARES ? smem_u32(smem + kb * 2 * L::A_TILE) : st;
+                const uint64_t a_hi = make_smem_desc(a_base), a_lo = make_smem_desc(a_base + L::A_TILE);
+                const uint64_t b_hi = make_smem_desc(st + L::B_OFF);
+                const uint64_t b_lo = make_smem_desc(st + L::B_OFF + L::B_TILE);
+                uint32_t accum = kb > kb0 ? 1u : 0u;
                 if (split) {      // small cross terms first, then the leading product
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -270,11 +323,12 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         const int q = warp - 4;                      // TMEM lane quarter owned by this warp
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int64_t t = t0; t < t1; ++t) {
             int64_t m_blk, n_blk;
-            tile_coords(t, m_blk, n_blk);
+            int slab;
+            tile_coords(t, m_blk, n_blk, slab);
             const int64_t row = m_blk * BM + q * 32 + lane;
-            epi.tile_begin(m_blk, n_blk, row);
+            epi.tile_begin(m_blk, n_blk, row, slab);
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);

@@ -262,6 +262,60 @@ class ScoreCEFn(torch.autograd.Function):
         return dH, dHpad, dW, db, dwpad, dbpad, None, None
 
 
+class ScoreCETcFn(torch.autograd.Function):
+    """Same contract as ScoreCEFn on the tcgen05 path: logits stay in tensor memory (forward keeps
+    per-tile log-sum-exp partials; backward recomputes, stores dZ as bf16 hi/lo and runs two more GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, H, Hpad, W, b, wpad, bpad, gt, rowscale, passes: int):
+        H, Hpad, W, b, wpad, bpad = (_f(t) for t in (H, Hpad, W, b, wpad, bpad))
+        gt, rowscale = gt.contiguous(), _f(rowscale)
+        M, d = H.shape
+        N = W.shape[0]
+        dev = H.device
+        zpad = torch.empty(M, device=dev, dtype=F32)
+        gemm(0, 1, M, 1, d, Hpad, d, wpad, d, zpad, 1, bias=bpad)
+        lse = torch.empty(M, device=dev, dtype=F32)
+        loss_row = torch.empty(M, device=dev, dtype=F32)
+        ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 0), dev)
+        call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, passes, ptr(lse),
+             ptr(loss_row), ptr(ws), ws.numel(), stream())
+        loss = torch.empty((), device=dev, dtype=F32)
+        call("c2dsr_wsum", ptr(loss_row), ptr(rowscale), M, ptr(loss), stream())
+        ctx.save_for_backward(H, Hpad, W, b, wpad, gt, rowscale, zpad, lse)
+        ctx.passes = passes
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        H, Hpad, W, b, wpad, gt, rowscale, zpad, lse = ctx.saved_tensors
+        M, d = H.shape
+        N = W.shape[0]
+        dev = H.device
+        coef = (rowscale * d_loss).contiguous()
+        dH = torch.empty(M, d, device=dev, dtype=F32)
+        dW = torch.zeros(N, d, device=dev, dtype=F32)
+        db = torch.zeros(N, device=dev, dtype=F32)
+        dzpad = torch.empty(M, device=dev, dtype=F32)
+        ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 1), dev)
+        call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d,
+             ctx.passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
+        dHpad = torch.empty(M, d, device=dev, dtype=F32)
+        gemm(0, 0, M, d, 1, dzpad, 1, wpad, d, dHpad, d)
+        dwpad = torch.empty(1, d, device=dev, dtype=F32)
+        gemm(1, 0, 1, d, M, dzpad, 1, Hpad, d, dwpad, d)
+        dbpad = torch.empty(1, device=dev, dtype=F32)
+        call("c2dsr_wsum", ptr(dzpad), None, M, ptr(dbpad), stream())
+        return dH, dHpad, dW, db, dwpad, dbpad, None, None, None
+
+
+def score_ce(H, Hpad, W, b, wpad, bpad, gt, rowscale, path: str = "tc", passes: int = 3):
+    """Weighted cross-entropy sum over the full catalogue; path 'tc' (tcgen05) or 'ffma' (fp32 CUDA cores)."""
+    if path == "tc":
+        return ScoreCETcFn.apply(H, Hpad, W, b, wpad, bpad, gt, rowscale, passes)
+    return ScoreCEFn.apply(H, Hpad, W, b, wpad, bpad, gt, rowscale)
+
+
 # ------------------------------------------------------------------------------------------------
 # K4b: scoring + rank counting (trainer.py:168-179)
 # ------------------------------------------------------------------------------------------------

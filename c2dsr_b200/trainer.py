@@ -148,8 +148,8 @@ class Trainer(object):
             Hpad = torch.cat((hs, h_dom), 0)                   # pad logit:   h_share | h_dom      (Q5)
             gt = torch.cat((g_share[:, -R:].reshape(-1), g_dom), 0)
             w = torch.cat((share_w, (1.0 / n_dom).expand(B * R)), 0)   # loss_share re-weighting (Q11)
-            parts.append(ops.ScoreCEFn.apply(H, Hpad, cls.weight, cls.bias, m.classifier_pad.weight,
-                                             m.classifier_pad.bias, gt, w))
+            parts.append(ops.score_ce(H, Hpad, cls.weight, cls.bias, m.classifier_pad.weight, m.classifier_pad.bias,
+                                      gt, w, path=self.score_path, passes=self.tc_passes))
         loss_rec = parts[0] + parts[1]
         loss = self.lambda_loss * loss_rec + (1 - self.lambda_loss) * loss_mi
         return loss, loss_rec, loss_mi

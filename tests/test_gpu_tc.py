@@ -74,3 +74,34 @@ def test_sharded_counts_add_up():
     for ws, n0, n1 in splits:
         ops.score_rank_tc(Qd, ws, bd[n0:n1].contiguous(), gtd, n0, n1, s_gt=s_sum, counts=counts)
     assert torch.equal(counts, full)
+
+
+@pytest.mark.parametrize("M,N,d,passes", [(200, 777, 64, 3), (640, 2903, 256, 3), (256, 50, 32, 3), (5120, 29207, 256, 3),
+                                          (640, 2903, 256, 1)])
+def test_score_ce_tc_vs_oracle(M, N, d, passes):
+    """Cross-entropy over the full catalogue on tensor cores vs plain fp32 (trainer.py:131-152).
+    Loss within 1e-5 (north star 1e-4); gradients within 1e-4 of their scale for the 3-pass split."""
+    from c2dsr_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    H, Hp = torch.randn(M, d, generator=g), torch.randn(M, d, generator=g)
+    Wt = torch.randn(N, d, generator=g) * 0.1
+    b = torch.randn(N, generator=g) * 0.1
+    wp, bp = torch.randn(1, d, generator=g) * 0.1, torch.randn(1, generator=g)
+    gt = torch.randint(0, N + 1, (M,), generator=g)
+    gt[:7] = N
+    rs = torch.rand(M, generator=g) / M
+    leaves = [t.clone().double().requires_grad_(True) for t in (H, Hp, Wt, b, wp, bp)]
+    Hc, Hpc, Wc, bc, wpc, bpc = leaves
+    z = torch.cat((Hc @ Wc.t() + bc, Hpc @ wpc.t() + bpc), -1)
+    lse = torch.logsumexp(z, -1)
+    picked = z.gather(1, gt.clamp(max=N).unsqueeze(1)).squeeze(1)
+    ref = (((lse - picked) * (gt != N)) * rs.double()).sum()
+    (ref * 0.7).backward()
+    dl = [t.to(DEV).requires_grad_(True) for t in (H, Hp, Wt, b, wp, bp)]
+    loss = ops.score_ce(*dl, gt.to(DEV), rs.to(DEV), path="tc", passes=passes)
+    tol_l, tol_g = (1e-5, 1e-4) if passes == 3 else (2e-3, 3e-2)
+    assert abs(float(loss.detach()) - float(ref)) <= tol_l * abs(float(ref))
+    (loss * 0.7).backward()
+    for got, r, nm in zip(dl, leaves, ("dH", "dHpad", "dW", "db", "dwpad", "dbpad")):
+        err = float((got.grad.cpu().double() - r.grad).abs().max()) / float(r.grad.abs().max())
+        assert err < tol_g, (nm, err)
