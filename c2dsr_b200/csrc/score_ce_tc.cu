@@ -8,6 +8,7 @@
 //           and stores it as bf16 hi/lo in both orientations ([M, N] and [N, M]); two more tcgen05 GEMMs
 //           give dH = dZ W (K = N) and dW += dZ^T H (K = M); db is a row sum of dZ^T.
 // All reductions have a fixed order (per-tile partials, ordered combines), so results are deterministic.
+#include <cuda_bf16.h>
 #include "tc_host.cuh"
 #include "../../include/c2dsr_b200.h"
 
@@ -24,34 +25,48 @@ struct LseEpilogue {
     int64_t M, N, n_blocks;
     float m_run, s_run;
     int64_t g, nb;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t n_blk, int64_t row, int) {
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t n_blk, int64_t row, int, int part) {
         m_run = -INFINITY;
         s_run = 0.f;
-        nb = n_blk;
+        nb = n_blk * tc::EPI_PARTS + part;                   // one (max, sum) pair per row, tile and column part
         g = row < M ? gt[row] : -1;
     }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M) return;
         float z[32];
         float cm = -INFINITY;
+        if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int64_t c = col0 + i;
-            if (c < N) {
-                z[i] = v[i] + __ldg(bias + c);
-                cm = fmaxf(cm, z[i]);
-                if (c == g) zgt[row] = z[i];
-            } else {
-                z[i] = -INFINITY;
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                z[4 * j] = v[4 * j] + b.x; z[4 * j + 1] = v[4 * j + 1] + b.y;
+                z[4 * j + 2] = v[4 * j + 2] + b.z; z[4 * j + 3] = v[4 * j + 3] + b.w;
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) z[i] = col0 + i < N ? v[i] + __ldg(bias + col0 + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cm = fmaxf(cm, z[i]);
+        if (g >= col0 && g < col0 + 32) {                    // target logit lives in this chunk
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i == g) zgt[row] = z[i];
         }
         if (cm == -INFINITY) return;                         // chunk entirely past N
         const float new_m = fmaxf(m_run, cm);
-        float s = s_run * exp2f((m_run - new_m) * kLog2e);   // first chunk: 0 * exp2(-inf) = 0
+        const float off = new_m * kLog2e;
+        float s0 = s_run * tc::ex2_approx((m_run - new_m) * kLog2e), s1 = 0.f, s2 = 0.f, s3 = 0.f;   // first chunk: 0 * 0
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s += exp2f((z[i] - new_m) * kLog2e);
+        for (int i = 0; i < 32; i += 4) {
+            s0 += tc::ex2_approx(fmaf(z[i], kLog2e, -off));
+            s1 += tc::ex2_approx(fmaf(z[i + 1], kLog2e, -off));
+            s2 += tc::ex2_approx(fmaf(z[i + 2], kLog2e, -off));
+            s3 += tc::ex2_approx(fmaf(z[i + 3], kLog2e, -off));
+        }
         m_run = new_m;
-        s_run = s;
+        s_run = (s0 + s1) + (s2 + s3);
     }
     __device__ __forceinline__ void tile_end(int64_t row) {
         if (row < M) {
@@ -94,50 +109,67 @@ struct GradEpilogue {
     uint16_t *dz_hi, *dz_lo;      // [M, ldn]
     uint16_t *dzt_hi, *dzt_lo;    // [N, ldm]
     int64_t M, N, ldn, ldm;
-    float l, cf;
+    float l2, cf;             // lse * log2(e), row coefficient
     int64_t g;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int) {
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int, int) {
         if (row < M) {
             g = gt[row];
-            l = lse[row];
+            l2 = lse[row] * kLog2e;
             cf = (g >= 0 && g < N) ? coef[row] : 0.f;
         }
     }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M || col0 >= ldn) return;
-        uint16_t hi[32], lo[32];
+        float dz[32];
+        if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                dz[4 * j] = v[4 * j] + b.x; dz[4 * j + 1] = v[4 * j + 1] + b.y;
+                dz[4 * j + 2] = v[4 * j + 2] + b.z; dz[4 * j + 3] = v[4 * j + 3] + b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dz[i] = col0 + i < N ? v[i] + __ldg(bias + col0 + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dz[i] = tc::ex2_approx(fmaf(dz[i], kLog2e, -l2)) * cf;     // softmax * coef; 0 past N
+        if (g >= col0 && g < col0 + 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i == g) dz[i] -= cf;                                              // minus onehot * coef
+        }
+        // bf16 hi / lo pairs, packed two columns per register
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(dz[2 * j], dz[2 * j + 1]);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            const float r0 = dz[2 * j] - __uint_as_float(hi[j] << 16);
+            const float r1 = dz[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u);
+            const __nv_bfloat162 q = __floats2bfloat162_rn(r0, r1);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&q);
+        }
+        // transposed copy dZ^T[c, row]: the 32 lanes of the warp write 32 consecutive rows of one column
+        const int n_valid = N - col0 < 32 ? (int)(N - col0) : 32;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-            const int64_t c = col0 + i;
-            float dz = 0.f;
-            if (c < N) {
-                float p = exp2f((v[i] + __ldg(bias + c) - l) * kLog2e);
-                if (c == g) p -= 1.f;
-                dz = p * cf;
-            }
-            split2(dz, hi[i], lo[i]);
-            if (c < N) {
-                dzt_hi[c * ldm + row] = hi[i];
-                if (dzt_lo) dzt_lo[c * ldm + row] = lo[i];
+            if (i < n_valid) {
+                const int64_t o = (col0 + i) * ldm + row;
+                dzt_hi[o] = (uint16_t)((i & 1) ? (hi[i >> 1] >> 16) : (hi[i >> 1] & 0xffffu));
+                if (dzt_lo) dzt_lo[o] = (uint16_t)((i & 1) ? (lo[i >> 1] >> 16) : (lo[i >> 1] & 0xffffu));
             }
         }
         // row-major copy: 8 bf16 per 16-byte store (ldn is a multiple of 8, col0 of 32)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             if (col0 + 8 * j < ldn) {
-                uint4 ph, pl;
-                ph.x = hi[8 * j] | ((uint32_t)hi[8 * j + 1] << 16);
-                ph.y = hi[8 * j + 2] | ((uint32_t)hi[8 * j + 3] << 16);
-                ph.z = hi[8 * j + 4] | ((uint32_t)hi[8 * j + 5] << 16);
-                ph.w = hi[8 * j + 6] | ((uint32_t)hi[8 * j + 7] << 16);
-                *reinterpret_cast<uint4*>(dz_hi + row * ldn + col0 + 8 * j) = ph;
-                if (dz_lo) {
-                    pl.x = lo[8 * j] | ((uint32_t)lo[8 * j + 1] << 16);
-                    pl.y = lo[8 * j + 2] | ((uint32_t)lo[8 * j + 3] << 16);
-                    pl.z = lo[8 * j + 4] | ((uint32_t)lo[8 * j + 5] << 16);
-                    pl.w = lo[8 * j + 6] | ((uint32_t)lo[8 * j + 7] << 16);
-                    *reinterpret_cast<uint4*>(dz_lo + row * ldn + col0 + 8 * j) = pl;
-                }
+                *reinterpret_cast<uint4*>(dz_hi + row * ldn + col0 + 8 * j) =
+                    make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                if (dz_lo)
+                    *reinterpret_cast<uint4*>(dz_lo + row * ldn + col0 + 8 * j) =
+                        make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
         }
     }
@@ -150,7 +182,7 @@ struct StoreEpilogue {       // slab s of a split-K GEMM goes to C + s * slab_st
     int accumulate;
     int64_t slab_stride;
     float* base;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int slab) { base = C + slab * slab_stride; }
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int slab, int) { base = C + slab * slab_stride; }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M) return;
         float* c = base + row * ldc + col0;
@@ -221,7 +253,7 @@ static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, int BN, bool ba
     CeLayout L;
     L.ldn = align_up(N, 8);
     L.ldm = align_up(M, 8);
-    L.n_blocks = ceil_div(N, BN);
+    L.n_blocks = ceil_div(N, BN) * tc::EPI_PARTS;          // (max, sum) pairs per row: one per tile and column part
     char* p = (char*)ws;
     auto take = [&](int64_t bytes) {
         char* q = p;

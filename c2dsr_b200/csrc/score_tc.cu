@@ -89,7 +89,7 @@ struct CountEpilogue {
     float tgt;
     int64_t g_local;
     int cnt;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int) {
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int, int) {
         cnt = 0;
         if (row < M) {
             tgt = s_gt[row];
@@ -98,6 +98,18 @@ struct CountEpilogue {
     }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M) return;
+        if (col0 + 32 <= N && !S_debug && (g_local < col0 || g_local >= col0 + 32) &&
+            (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
+            // interior chunk without the target: add the bias, compare, count
+            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(b4 + j);
+                cnt += (v[4 * j] + b.x > tgt) + (v[4 * j + 1] + b.y > tgt) + (v[4 * j + 2] + b.z > tgt) +
+                       (v[4 * j + 3] + b.w > tgt);
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int64_t c = col0 + i;
@@ -117,7 +129,7 @@ struct DiagEpilogue {       // BN == BM: element (row, row) of tile (b, b)
     const float* bias_gt;    // [M]
     float* s_gt;             // [M]
     int64_t M;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int) {}
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int, int) {}
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M || row < col0 || row >= col0 + 32) return;
         const int want = (int)(row - col0);

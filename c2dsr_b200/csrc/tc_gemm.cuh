@@ -9,7 +9,8 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem, mbarrier expect_tx
 //   warp 1      MMA issuer     one lane issues tcgen05.mma (M = 128, N = BN, K = 16), commits to mbarriers
 //   warp 2      TMEM allocator 2 accumulator stages x BN columns
-//   warps 4..7  epilogue       tcgen05.ld 32 lanes x 32 columns at a time; the functor consumes rows
+//   warps 4..11 epilogue       tcgen05.ld 32 lanes x 32 columns at a time; the functor consumes rows
+//                              (two warps per TMEM lane quarter, each owns half of the tile's columns)
 // so the epilogue of tile i overlaps the MMAs of tile i+1 and the TMA loads of tile i+2.
 //
 // Two operand-staging modes:
@@ -30,6 +31,16 @@ constexpr int BM = 128;        // rows of A per tile = TMEM lanes
 constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int ARES_MAX_KB = 4; // resident A: up to 4 k-blocks (K <= 256)
+constexpr int EPI_WARPS = 8;   // epilogue warps: two per TMEM lane quarter, each takes half of the tile's columns
+constexpr int EPI_PARTS = EPI_WARPS / 4;
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
+
+// ex2.approx: 2 ulp, maps -inf to +0 (what the online soft-max needs)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -154,11 +165,12 @@ struct SmemLayout {
 };
 
 // Epilogue functor contract (one instance per epilogue thread; the thread owns A row `row`):
-//   void tile_begin(int64_t m_blk, int64_t n_blk, int64_t row, int k_slab);
+//   void tile_begin(int64_t m_blk, int64_t n_blk, int64_t row, int k_slab, int part);
 //   void chunk(int64_t row, int64_t col0, const float (&v)[32]);   // columns col0..col0+31 of the tile
 //   void tile_end(int64_t row);
+// Each row of a tile is shared by EPI_PARTS threads (`part` = which BN / EPI_PARTS column range they own).
 template <int BN, int STAGES, bool ARES, class Epilogue>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
     using L = SmemLayout<BN, STAGES, ARES>;
     extern __shared__ uint8_t smem_raw[];
@@ -198,7 +210,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full[s], 1);
-            mbar_init(&tmem_empty[s], 4);
+            mbar_init(&tmem_empty[s], EPI_WARPS);
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
@@ -320,7 +332,9 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         }
     } else if (warp >= 4) {
         // ---------------- epilogue ----------------
-        const int q = warp - 4;                      // TMEM lane quarter owned by this warp
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access (warp id mod 4)
+        const int part = (warp - 4) >> 2;            // which column range of the tile
+        constexpr int PART_COLS = BN / EPI_PARTS;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t t = t0; t < t1; ++t) {
@@ -328,15 +342,15 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             int slab;
             tile_coords(t, m_blk, n_blk, slab);
             const int64_t row = m_blk * BM + q * 32 + lane;
-            epi.tile_begin(m_blk, n_blk, row, slab);
+            epi.tile_begin(m_blk, n_blk, row, slab, part);
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + part * PART_COLS);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < PART_COLS / 32; ++c) {
                 float v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                epi.chunk(row, n_blk * BN + c * 32, v);
+                epi.chunk(row, n_blk * BN + part * PART_COLS + c * 32, v);
             }
             tcgen05_fence_before();
             __syncwarp();

@@ -89,7 +89,7 @@ static inline int launch_gemm(const tc::Maps& maps, const tc::Problem& pb, const
     const int64_t tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks * (pb.k_splits > 1 ? pb.k_splits : 1);
     if (tiles <= 0) return C2DSR_OK;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, 256, L::TOTAL, st>>>(maps, pb, epi);
+    kern<<<grid, tc::THREADS, L::TOTAL, st>>>(maps, pb, epi);
     note_launches(1);
     return check_launch("tc_gemm");
 }
