@@ -43,13 +43,16 @@ _PROTOS = {
     "c2dsr_gemm_workspace_bytes": (i64, [i64, i64, i64]),
     "c2dsr_gemm": (i32, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, vp, i32] + _DROP
                    + [vp, i64, vp]),
+    "c2dsr_gemm_tc_workspace_bytes": (i64, [i64, i64, i64]),
+    "c2dsr_gemm_tc": (i32, [i32, i32, i64, i64, i64, vp, i64, vp, i64, f32, vp, i64, vp, i32] + _DROP
+                      + [i32, vp, i64, vp]),
     "c2dsr_colsum": (i32, [vp, i64, i64, i64, vp, i32, vp, i64, vp]),
     "c2dsr_wsum": (i32, [vp, vp, i64, vp, vp]),
     "c2dsr_encoder_saved_floats": (i64, [i64, i32, i32, i32]),
-    "c2dsr_encoder_workspace_bytes": (i64, [i64, i32, i32]),
-    "c2dsr_encoder_fwd": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, f32] + _DROP
+    "c2dsr_encoder_workspace_bytes": (i64, [i64, i32, i32, i32]),
+    "c2dsr_encoder_fwd": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32] + _DROP
                           + [vp, vp, vp, i64, vp]),
-    "c2dsr_encoder_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, f32] + _DROP
+    "c2dsr_encoder_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32] + _DROP
                           + [vp, vp, vp, i64, vp]),
     "c2dsr_attention_fwd": (i32, [vp, vp, i64, i32, i32, i32, i64] + _DROP + [vp, vp, vp]),
     "c2dsr_attention_bwd": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, i64] + _DROP + [vp, vp]),

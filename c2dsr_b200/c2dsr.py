@@ -38,6 +38,11 @@ class SelfAttention(nn.Module):
         self.n_head = args.n_head
         self.norm_first = bool(args.norm_first)
         self.p = args.dropout_attn
+        # dense layers of the encoder: fp32 FFMA (0, default) or tcgen05 with the bf16 hi/lo split (3) / plain
+        # bf16 (1).  The default keeps the ReLU masks of the feed-forward bit-compatible with fp32: a 1e-5
+        # perturbation of a pre-activation flips a handful of units per batch, which shows up as O(1e-3)
+        # element-wise gradient differences although the loss is unaffected.
+        self.dense_passes = int(getattr(args, "encoder_tc_passes", 0))
         self.register_buffer("attn_mask", nn.Transformer.generate_square_subsequent_mask(args.len_max))
         self.dropout_attn = nn.Dropout(p=args.dropout_attn)
         self.pos_emb = nn.Embedding(args.len_max, args.d_latent)
@@ -60,7 +65,8 @@ class SelfAttention(nn.Module):
     def encode(self, seq, x, seed: int, tag: int):
         """x already holds sqrt(d) * (hi[seq] + E[seq]) + P[pos] with input dropout applied."""
         p = self.p if self.training else 0.0
-        return ops.EncoderFn.apply(x, seq, self.n_head, self.idx_pad, self.norm_first, p, seed, tag, *self.weights())
+        return ops.EncoderFn.apply(x, seq, self.n_head, self.idx_pad, self.norm_first, p, seed, tag,
+                                   self.dense_passes, *self.weights())
 
 
 class C2DSR(nn.Module):

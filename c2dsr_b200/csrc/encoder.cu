@@ -15,6 +15,30 @@ int gemm_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, 
                   const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act,
                   Dropout dr, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
+int gemm_tc_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                     int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act, Dropout dr, int passes,
+                     void* workspace, int64_t workspace_bytes, cudaStream_t st);
+int64_t gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+// dense layer product: tcgen05 path (passes = 1 or 3) or the fp32 FFMA kernel (passes = 0); alpha is always 1
+static int dense(int passes, void* tws, int64_t tws_bytes, int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha,
+                 const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C, int64_t ldc,
+                 const float* bias, int act, Dropout dr, void* gws, int64_t gws_bytes, cudaStream_t st) {
+    if (passes == 0) return gemm_dispatch(ta, tb, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, act, dr, gws, gws_bytes, st);
+    return gemm_tc_dispatch(ta, tb, M, N, K, A, lda, B, ldb, beta, C, ldc, bias, act, dr, passes, tws, tws_bytes, st);
+}
+
+// scratch of the tcgen05 dense path: the largest of the five products of a layer
+static int64_t dense_tc_bytes(int64_t T, int d) {
+    int64_t b = gemm_tc_workspace_bytes(T, 3 * d, d);
+    const int64_t shapes[4][3] = {{T, d, d}, {T, d, 3 * d}, {3 * d, d, T}, {d, d, T}};
+    for (auto& s : shapes) {
+        const int64_t x = gemm_tc_workspace_bytes(s[0], s[1], s[2]);
+        if (x > b) b = x;
+    }
+    return b;
+}
+
 constexpr int kMaxPerLane = 16;   // features per lane: d (or head dim) <= 512
 constexpr int64_t kGemmWsBytes = 16ll << 20;   // split-K partials / column-reduction partials
 constexpr int kLnChunk = 128;
@@ -503,26 +527,29 @@ int64_t c2dsr_encoder_saved_floats(int64_t n_tok, int d, int n_head, int n_layer
     return n_layers * layer_floats(n_tok, d, n_head) + n_tok * ((int64_t)d + 2);
 }
 
-int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head) {
+int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head, int dense_passes) {
     (void)n_head;
-    return 7 * n_tok * (int64_t)d * 4 + kGemmWsBytes + 1024;
+    return 7 * n_tok * (int64_t)d * 4 + kGemmWsBytes + (dense_passes ? dense_tc_bytes(n_tok, d) : 0) + 1024;
 }
 
 int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
                       const float* x, const int64_t* seq, int64_t n_seq, int L, int d, int n_head, int64_t pad_idx,
-                      int norm_first, float eps, float p, uint64_t seed, uint64_t tag, float* out, float* saved,
-                      void* workspace, int64_t workspace_bytes, void* stream) {
+                      int norm_first, int dense_passes, float eps, float p, uint64_t seed, uint64_t tag, float* out,
+                      float* saved, void* workspace, int64_t workspace_bytes, void* stream) {
     if (n_seq <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
     C2DSR_REQUIRE(n_head > 0 && d % n_head == 0, "d must be divisible by n_head");
     const int64_t T = n_seq * L;
-    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head)) {
+    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head, dense_passes)) {
         set_error("encoder_fwd: workspace too small");
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     float* ybuf = (float*)workspace;
     void* gws = (char*)workspace + 7 * T * (int64_t)d * 4;
+    void* tws = (char*)gws + kGemmWsBytes;
+    const int64_t tws_bytes = dense_passes ? dense_tc_bytes(T, d) : 0;
+    C2DSR_REQUIRE(dense_passes == 0 || dense_passes == 1 || dense_passes == 3, "dense_passes must be 0, 1 or 3");
     const Dropout none = make_dropout(0.f, 0, 0);
     const AttnShape sh = make_shape(n_seq, L, d, n_head, pad_idx);
     const int64_t lf = layer_floats(T, d, n_head);
@@ -542,10 +569,10 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const flo
             RUN(launch_add_ln(s.xin, nullptr, w.ln1_w, w.ln1_b, nullptr, s.s1, s.st1, T, d, 1, eps, none, st));
             attn_in = s.s1;
         }
-        RUN(gemm_dispatch(0, 1, T, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, s.qkv, 3 * d, w.in_proj_b, 0, none,
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 1, T, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, s.qkv, 3 * d, w.in_proj_b, 0, none,
                           gws, kGemmWsBytes, st));
         RUN(launch_attn_fwd(s.qkv, seq, sh, make_dropout(p, seed, tb + 0), s.o, s.lse, st));
-        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, s.o, d, w.out_proj_w, d, 0.f, ybuf, d, w.out_proj_b, 0, none, gws,
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 1, T, d, d, 1.f, s.o, d, w.out_proj_w, d, 0.f, ybuf, d, w.out_proj_b, 0, none, gws,
                           kGemmWsBytes, st));
         const float* ffn_in;
         if (norm_first) {
@@ -558,9 +585,9 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const flo
                               make_dropout(p, seed, tb + 1), st));
             ffn_in = s.x1;
         }
-        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, ffn_in, d, w.lin1_w, d, 0.f, s.fd, d, w.lin1_b, 1,
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 1, T, d, d, 1.f, ffn_in, d, w.lin1_w, d, 0.f, s.fd, d, w.lin1_b, 1,
                           make_dropout(p, seed, tb + 2), gws, kGemmWsBytes, st));
-        RUN(gemm_dispatch(0, 1, T, d, d, 1.f, s.fd, d, w.lin2_w, d, 0.f, ybuf, d, w.lin2_b, 0, none, gws,
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 1, T, d, d, 1.f, s.fd, d, w.lin2_w, d, 0.f, ybuf, d, w.lin2_b, 0, none, gws,
                           kGemmWsBytes, st));
         if (norm_first) {
             RUN(launch_add_ln(s.x1, ybuf, nullptr, nullptr, nullptr, next, nullptr, T, d, 0, eps,
@@ -576,14 +603,14 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const flo
 
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads* grads, int n_layers,
                       const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,
-                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, float eps, float p,
-                      uint64_t seed, uint64_t tag, const float* saved_c, float* dx, void* workspace,
-                      int64_t workspace_bytes, void* stream) {
+                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, int dense_passes,
+                      float eps, float p, uint64_t seed, uint64_t tag, const float* saved_c, float* dx,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
     (void)eps;
     if (n_seq <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
     const int64_t T = n_seq * L;
-    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head)) {
+    if (workspace_bytes < c2dsr_encoder_workspace_bytes(T, d, n_head, dense_passes)) {
         set_error("encoder_bwd: workspace too small");
         return C2DSR_ERR_WORKSPACE;
     }
@@ -596,6 +623,8 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
     float* dfd = dy + Td;
     float* dqkv = dfd + Td;              // [T, 3d]
     void* gws = (char*)workspace + 7 * Td * 4;
+    void* tws = (char*)gws + kGemmWsBytes;
+    const int64_t tws_bytes = dense_passes ? dense_tc_bytes(T, d) : 0;
     const Dropout none = make_dropout(0.f, 0, 0);
     const AttnShape sh = make_shape(n_seq, L, d, n_head, pad_idx);
     const int64_t lf = layer_floats(T, d, n_head);
@@ -629,22 +658,22 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         }
         const float* d_y2 = masked(d_s2, 3);
         const float* ffn_in = norm_first ? s.s2 : s.x1;
-        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y2, d, s.fd, d, 1.f, gw.lin2_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 1, 0, d, d, T, 1.f, d_y2, d, s.fd, d, 1.f, gw.lin2_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_colsum_acc(gws, d_y2, T, d, gw.lin2_b, st));
-        RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y2, d, w.lin2_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, d, 1.f, d_y2, d, w.lin2_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         relu_drop_bwd_kernel<<<ew_blocks(Td), 256, 0, st>>>(dfd, s.fd, Td, inv_keep);
         note_launches(1);
-        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, dfd, d, ffn_in, d, 1.f, gw.lin1_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 1, 0, d, d, T, 1.f, dfd, d, ffn_in, d, 1.f, gw.lin1_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_colsum_acc(gws, dfd, T, d, gw.lin1_b, st));
         // gradient w.r.t. x1 (post-norm: d_s2 + d_pre W1; pre-norm: g + LN2^T(d_pre W1))
         float* d_x1;
         if (norm_first) {
-            RUN(gemm_dispatch(0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
             RUN(launch_ln_param(gws, ds, s.x1, s.st2, gw.ln2_w, gw.ln2_b, T, d, st));
             RUN(launch_ln_bwd(ds, s.x1, s.st2, w.ln2_w, g, 1, T, d, st));
             d_x1 = g;
         } else {
-            RUN(gemm_dispatch(0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 1.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, d, 1.f, dfd, d, w.lin1_w, d, 1.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
             d_x1 = ds;
         }
         // ---- attention block ----
@@ -658,18 +687,18 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         }
         const float* d_y = masked(d_s1, 1);
         const float* attn_in = norm_first ? s.s1 : s.xin;
-        RUN(gemm_dispatch(1, 0, d, d, T, 1.f, d_y, d, s.o, d, 1.f, gw.out_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 1, 0, d, d, T, 1.f, d_y, d, s.o, d, 1.f, gw.out_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_colsum_acc(gws, d_y, T, d, gw.out_proj_b, st));
-        RUN(gemm_dispatch(0, 0, T, d, d, 1.f, d_y, d, w.out_proj_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, d, 1.f, d_y, d, w.out_proj_w, d, 0.f, dfd, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_attn_bwd(s.qkv, s.o, s.lse, dfd, seq, sh, make_dropout(p, seed, tb + 0), dqkv, st));
-        RUN(gemm_dispatch(1, 0, 3 * d, d, T, 1.f, dqkv, 3 * d, attn_in, d, 1.f, gw.in_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+        RUN(dense(dense_passes, tws, tws_bytes, 1, 0, 3 * d, d, T, 1.f, dqkv, 3 * d, attn_in, d, 1.f, gw.in_proj_w, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         RUN(launch_colsum_acc(gws, dqkv, T, 3 * d, gw.in_proj_b, st));
         if (norm_first) {
-            RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 0.f, ds, d, nullptr, 0, none, gws, kGemmWsBytes, st));
             RUN(launch_ln_param(gws, ds, s.xin, s.st1, gw.ln1_w, gw.ln1_b, T, d, st));
             RUN(launch_ln_bwd(ds, s.xin, s.st1, w.ln1_w, g, 1, T, d, st));
         } else {
-            RUN(gemm_dispatch(0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 1.f, g, d, nullptr, 0, none, gws, kGemmWsBytes, st));
+            RUN(dense(dense_passes, tws, tws_bytes, 0, 0, T, d, 3 * d, 1.f, dqkv, 3 * d, w.in_proj_w, d, 1.f, g, d, nullptr, 0, none, gws, kGemmWsBytes, st));
         }
         // g now holds the gradient w.r.t. this layer's input
     }

@@ -2,12 +2,13 @@
 // reference) without ever materialising the fp32 logits.
 //
 // forward   Z = H W^T + b tile by tile in tensor memory (tcgen05, bf16 hi/lo split, fp32 accumulate);
-//           the epilogue keeps, per row and tile, an online (max, sum exp) pair and picks the target
-//           logit; a small kernel combines the per-tile pairs (+ the pad logit) into lse and loss.
+//           the epilogue keeps, per row and tile part, an online (max, sum exp) pair and picks the target
+//           logit; a small kernel combines the pairs (+ the pad logit) into lse and loss.
 // backward  the same GEMM is recomputed; its epilogue turns each tile into dZ = (softmax - onehot) * coef
-//           and stores it as bf16 hi/lo in both orientations ([M, N] and [N, M]); two more tcgen05 GEMMs
-//           give dH = dZ W (K = N) and dW += dZ^T H (K = M); db is a row sum of dZ^T.
-// All reductions have a fixed order (per-tile partials, ordered combines), so results are deterministic.
+//           and stores it once, row-major [M, N], as bf16 hi/lo.  Two more tcgen05 GEMMs read it in both
+//           orientations without a transposed copy: dH = dZ W (dZ K-major, W MN-major, K = N) and
+//           dW += dZ^T H (dZ and H MN-major, K = M).  db is a column sum of dZ.
+// All reductions have a fixed order (per-tile partials, K slabs added in order), so results are deterministic.
 #include <cuda_bf16.h>
 #include "tc_host.cuh"
 #include "../../include/c2dsr_b200.h"
@@ -16,37 +17,42 @@ namespace c2dsr {
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+__device__ __forceinline__ void add_bias32(const float (&v)[32], const float* __restrict__ bias, int64_t col0,
+                                           int64_t N, float (&z)[32]) {
+    if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            z[4 * j] = v[4 * j] + b.x; z[4 * j + 1] = v[4 * j + 1] + b.y;
+            z[4 * j + 2] = v[4 * j + 2] + b.z; z[4 * j + 3] = v[4 * j + 3] + b.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = col0 + i < N ? v[i] + __ldg(bias + col0 + i) : -INFINITY;   // past N: -inf
+    }
+}
+
 struct LseEpilogue {
     const float* bias;        // [N]
     const int64_t* gt;        // [M], N = ignored
-    float* pmax;              // [M, n_blocks]
-    float* psum;              // [M, n_blocks]
-    float* zgt;               // [M] target logit (written by the tile that holds it)
-    int64_t M, N, n_blocks;
+    float* pmax;              // [M, n_pairs]
+    float* psum;              // [M, n_pairs]
+    float* zgt;               // [M] target logit (written by the thread that holds it)
+    int64_t M, N, n_pairs;
     float m_run, s_run;
-    int64_t g, nb;
+    int64_t g, slot;
     __device__ __forceinline__ void tile_begin(int64_t, int64_t n_blk, int64_t row, int, int part) {
         m_run = -INFINITY;
         s_run = 0.f;
-        nb = n_blk * tc::EPI_PARTS + part;                   // one (max, sum) pair per row, tile and column part
+        slot = n_blk * tc::EPI_PARTS + part;                 // one (max, sum) pair per row, tile and column part
         g = row < M ? gt[row] : -1;
     }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M) return;
         float z[32];
+        add_bias32(v, bias, col0, N, z);
         float cm = -INFINITY;
-        if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(b4 + j);
-                z[4 * j] = v[4 * j] + b.x; z[4 * j + 1] = v[4 * j + 1] + b.y;
-                z[4 * j + 2] = v[4 * j + 2] + b.z; z[4 * j + 3] = v[4 * j + 3] + b.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) z[i] = col0 + i < N ? v[i] + __ldg(bias + col0 + i) : -INFINITY;
-        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) cm = fmaxf(cm, z[i]);
         if (g >= col0 && g < col0 + 32) {                    // target logit lives in this chunk
@@ -70,8 +76,8 @@ struct LseEpilogue {
     }
     __device__ __forceinline__ void tile_end(int64_t row) {
         if (row < M) {
-            pmax[row * n_blocks + nb] = m_run;
-            psum[row * n_blocks + nb] = s_run;
+            pmax[row * n_pairs + slot] = m_run;
+            psum[row * n_pairs + slot] = s_run;
         }
     }
 };
@@ -79,18 +85,18 @@ struct LseEpilogue {
 // one warp per row: lse over the per-tile pairs and the pad logit, then the row loss
 __global__ void lse_combine_kernel(const float* __restrict__ pmax, const float* __restrict__ psum,
                                    const float* __restrict__ zgt, const float* __restrict__ zpad,
-                                   const int64_t* __restrict__ gt, int64_t M, int64_t N, int64_t n_blocks,
+                                   const int64_t* __restrict__ gt, int64_t M, int64_t N, int64_t n_pairs,
                                    float* __restrict__ lse, float* __restrict__ loss_row) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const float zp = zpad[row];
     float m = zp;
-    for (int64_t b = lane; b < n_blocks; b += 32) m = fmaxf(m, pmax[row * n_blocks + b]);
+    for (int64_t b = lane; b < n_pairs; b += 32) m = fmaxf(m, pmax[row * n_pairs + b]);
     m = warp_max(m);
     float s = 0.f;
-    for (int64_t b = lane; b < n_blocks; b += 32)
-        s += psum[row * n_blocks + b] * exp2f((pmax[row * n_blocks + b] - m) * kLog2e);
+    for (int64_t b = lane; b < n_pairs; b += 32)
+        s += psum[row * n_pairs + b] * exp2f((pmax[row * n_pairs + b] - m) * kLog2e);   // empty part: 0 * exp2(-inf) = 0
     s = warp_sum(s);
     if (lane == 0) {
         s += exp2f((zp - m) * kLog2e);
@@ -106,9 +112,8 @@ struct GradEpilogue {
     const int64_t* gt;        // [M]
     const float* lse;         // [M]
     const float* coef;        // [M]
-    uint16_t *dz_hi, *dz_lo;      // [M, ldn]
-    uint16_t *dzt_hi, *dzt_lo;    // [N, ldm]
-    int64_t M, N, ldn, ldm;
+    uint16_t *dz_hi, *dz_lo;  // [M, ldn]
+    int64_t M, N, ldn;
     float l2, cf;             // lse * log2(e), row coefficient
     int64_t g;
     __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int, int) {
@@ -121,18 +126,7 @@ struct GradEpilogue {
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M || col0 >= ldn) return;
         float dz[32];
-        if (col0 + 32 <= N && (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(b4 + j);
-                dz[4 * j] = v[4 * j] + b.x; dz[4 * j + 1] = v[4 * j + 1] + b.y;
-                dz[4 * j + 2] = v[4 * j + 2] + b.z; dz[4 * j + 3] = v[4 * j + 3] + b.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dz[i] = col0 + i < N ? v[i] + __ldg(bias + col0 + i) : -INFINITY;
-        }
+        add_bias32(v, bias, col0, N, dz);
 #pragma unroll
         for (int i = 0; i < 32; ++i) dz[i] = tc::ex2_approx(fmaf(dz[i], kLog2e, -l2)) * cf;     // softmax * coef; 0 past N
         if (g >= col0 && g < col0 + 32) {
@@ -140,66 +134,43 @@ struct GradEpilogue {
             for (int i = 0; i < 32; ++i)
                 if (col0 + i == g) dz[i] -= cf;                                              // minus onehot * coef
         }
-        // bf16 hi / lo pairs, packed two columns per register
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const __nv_bfloat162 h = __floats2bfloat162_rn(dz[2 * j], dz[2 * j + 1]);
-            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
-            const float r0 = dz[2 * j] - __uint_as_float(hi[j] << 16);
-            const float r1 = dz[2 * j + 1] - __uint_as_float(hi[j] & 0xffff0000u);
-            const __nv_bfloat162 q = __floats2bfloat162_rn(r0, r1);
-            lo[j] = *reinterpret_cast<const uint32_t*>(&q);
-        }
-        // transposed copy dZ^T[c, row]: the 32 lanes of the warp write 32 consecutive rows of one column
-        const int n_valid = N - col0 < 32 ? (int)(N - col0) : 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (i < n_valid) {
-                const int64_t o = (col0 + i) * ldm + row;
-                dzt_hi[o] = (uint16_t)((i & 1) ? (hi[i >> 1] >> 16) : (hi[i >> 1] & 0xffffu));
-                if (dzt_lo) dzt_lo[o] = (uint16_t)((i & 1) ? (lo[i >> 1] >> 16) : (lo[i >> 1] & 0xffffu));
-            }
-        }
-        // row-major copy: 8 bf16 per 16-byte store (ldn is a multiple of 8, col0 of 32)
+        // bf16 hi / lo, two columns per register, 8 columns per 16-byte store (ldn % 8 == 0, col0 % 32 == 0)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (col0 + 8 * j < ldn) {
-                *reinterpret_cast<uint4*>(dz_hi + row * ldn + col0 + 8 * j) =
-                    make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                if (dz_lo)
-                    *reinterpret_cast<uint4*>(dz_lo + row * ldn + col0 + 8 * j) =
-                        make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            if (col0 + 8 * j >= ldn) break;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float a = dz[8 * j + 2 * k], b = dz[8 * j + 2 * k + 1];
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                hi[k] = *reinterpret_cast<const uint32_t*>(&h);
+                const __nv_bfloat162 q = __floats2bfloat162_rn(a - __uint_as_float(hi[k] << 16),
+                                                               b - __uint_as_float(hi[k] & 0xffff0000u));
+                lo[k] = *reinterpret_cast<const uint32_t*>(&q);
             }
+            *reinterpret_cast<uint4*>(dz_hi + row * ldn + col0 + 8 * j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (dz_lo) *reinterpret_cast<uint4*>(dz_lo + row * ldn + col0 + 8 * j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
     __device__ __forceinline__ void tile_end(int64_t) {}
 };
 
-struct StoreEpilogue {       // slab s of a split-K GEMM goes to C + s * slab_stride (C[row, c] = acc, or += acc)
+struct SlabEpilogue {        // slab s of a split-K GEMM goes to C + s * slab_stride, compact [M, N]
     float* C;
-    int64_t ldc, M, N;
-    int accumulate;
-    int64_t slab_stride;
+    int64_t M, N, slab_stride;
     float* base;
     __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t, int slab, int) { base = C + slab * slab_stride; }
     __device__ __forceinline__ void chunk(int64_t row, int64_t col0, const float (&v)[32]) {
         if (row >= M) return;
-        float* c = base + row * ldc + col0;
-        if (col0 + 32 <= N && (ldc & 3) == 0) {
+        float* c = base + row * N + col0;
+        if (col0 + 32 <= N && (N & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (accumulate) {
-                    const float4 old = reinterpret_cast<float4*>(c)[j];
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                reinterpret_cast<float4*>(c)[j] = o;
-            }
+            for (int j = 0; j < 8; ++j)
+                reinterpret_cast<float4*>(c)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (col0 + i < N) c[i] = accumulate ? c[i] + v[i] : v[i];
+                if (col0 + i < N) c[i] = v[i];
         }
     }
     __device__ __forceinline__ void tile_end(int64_t) {}
@@ -214,20 +185,28 @@ __global__ void slab_reduce_kernel(const float* __restrict__ part, int slabs, in
     }
 }
 
-// db[n] += sum_m dZ^T[n, m] (hi + lo), one warp per row, fixed order
-__global__ void rowsum_bf16_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t rows,
-                                   int64_t cols, int64_t ld, float* out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
+// db: column sums of dZ (hi + lo) in two phases: row chunks of 64 -> partial[chunk][col], then chunk order
+constexpr int kDbChunk = 64;
+__global__ void dz_colsum_partial_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t M,
+                                         int64_t N, int64_t ld, float* __restrict__ partial) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.y * kDbChunk, r1 = r0 + kDbChunk < M ? r0 + kDbChunk : M;
     float s = 0.f;
-    for (int64_t c = lane; c < cols; c += 32) {
+#pragma unroll 8
+    for (int64_t r = r0; r < r1; ++r) {
         float x = bf16_to_f32(hi[r * ld + c]);
         if (lo) x += bf16_to_f32(lo[r * ld + c]);
         s += x;
     }
-    s = warp_sum(s);
-    if (lane == 0) out[r] += s;
+    partial[(int64_t)blockIdx.y * N + c] = s;
+}
+__global__ void dz_colsum_final_kernel(const float* __restrict__ partial, int64_t n_chunks, int64_t N, float* out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    float s = 0.f;
+    for (int64_t k = 0; k < n_chunks; ++k) s += partial[k * N + c];
+    out[c] += s;
 }
 
 __global__ void dzpad_kernel(const float* __restrict__ zpad, const float* __restrict__ lse,
@@ -239,21 +218,22 @@ __global__ void dzpad_kernel(const float* __restrict__ zpad, const float* __rest
     dzpad[m] = (g >= 0 && g < N) ? expf(zpad[m] - lse[m]) * coef[m] : 0.f;
 }
 
+constexpr int kBN1 = 128, kStages1 = 3;     // logits GEMM (epilogue-heavy)
+constexpr int kBN2 = 256, kStages2 = 2;     // gradient GEMMs: one tile spans d = 256 so dZ is read once
+
 struct CeLayout {       // carve-up of the caller's workspace
-    uint16_t *h_hi, *h_lo, *w_hi, *w_lo;            // [M, d], [N, d]
-    uint16_t *ht_hi, *ht_lo, *wt_hi, *wt_lo;        // [d, ldm], [d, ldn]
-    uint16_t *dz_hi, *dz_lo, *dzt_hi, *dzt_lo;      // [M, ldn], [N, ldm]
+    uint16_t *h_hi, *h_lo, *w_hi, *w_lo;    // [M, d], [N, d]
+    uint16_t *dz_hi, *dz_lo;                // [M, ldn]
     float *pmax, *psum, *zgt;
-    float* slabs;                                    // split-K partial sums of the gradient GEMMs
-    int64_t ldn, ldm, n_blocks, bytes;
+    float* slabs;                           // split-K partial sums of the gradient GEMMs / db partials
+    int64_t ldn, n_pairs, bytes;
     int ks_dh, ks_dw;
 };
 
-static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, int BN, bool backward) {
+static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, bool backward) {
     CeLayout L;
     L.ldn = align_up(N, 8);
-    L.ldm = align_up(M, 8);
-    L.n_blocks = ceil_div(N, BN) * tc::EPI_PARTS;          // (max, sum) pairs per row: one per tile and column part
+    L.n_pairs = ceil_div(N, kBN1) * tc::EPI_PARTS;
     char* p = (char*)ws;
     auto take = [&](int64_t bytes) {
         char* q = p;
@@ -262,38 +242,33 @@ static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, int BN, bool ba
     };
     L.h_hi = (uint16_t*)take(M * d * 2); L.h_lo = (uint16_t*)take(M * d * 2);
     L.w_hi = (uint16_t*)take(N * d * 2); L.w_lo = (uint16_t*)take(N * d * 2);
-    L.pmax = (float*)take(M * L.n_blocks * 4); L.psum = (float*)take(M * L.n_blocks * 4);
+    L.pmax = (float*)take(M * L.n_pairs * 4); L.psum = (float*)take(M * L.n_pairs * 4);
     L.zgt = (float*)take(M * 4);
-    L.ht_hi = L.ht_lo = L.wt_hi = L.wt_lo = L.dz_hi = L.dz_lo = L.dzt_hi = L.dzt_lo = nullptr;
+    L.dz_hi = L.dz_lo = nullptr;
     L.slabs = nullptr;
     // K slabs: enough tiles to fill the SMs, and short accumulation chains in tensor memory
-    const int64_t tiles_dh = ceil_div(M, tc::BM) * ceil_div(d, 256), tiles_dw = ceil_div(N, tc::BM) * ceil_div(d, 256);
+    const int64_t tiles_dh = ceil_div(M, tc::BM) * ceil_div(d, kBN2), tiles_dw = ceil_div(N, tc::BM) * ceil_div(d, kBN2);
     auto pick = [](int64_t tiles, int64_t K) {
-        int64_t want = ceil_div(2 * 148, tiles > 0 ? tiles : 1);
-        int64_t by_k = ceil_div(K, 64 * 48);                  // at most ~48 k-blocks per slab
+        const int64_t want = ceil_div(2 * 148, tiles > 0 ? tiles : 1);
+        const int64_t by_k = ceil_div(K, 64 * 48);            // at most ~48 k-blocks per slab
         int64_t s = want > by_k ? want : by_k;
         const int64_t max_s = ceil_div(K, 64 * 4);            // at least 4 k-blocks per slab
         if (s > max_s) s = max_s;
         if (s > 16) s = 16;
-        return (int)(s < 1 ? 1 : s);
+        return effective_splits(K, s);
     };
     L.ks_dh = pick(tiles_dh, N);
     L.ks_dw = pick(tiles_dw, M);
     if (backward) {
-        const int64_t slab_floats = (int64_t)L.ks_dh * M * d > (int64_t)L.ks_dw * N * d ? (int64_t)L.ks_dh * M * d
-                                                                                        : (int64_t)L.ks_dw * N * d;
-        L.slabs = (float*)take(slab_floats * 4);
-        L.ht_hi = (uint16_t*)take(d * L.ldm * 2); L.ht_lo = (uint16_t*)take(d * L.ldm * 2);
-        L.wt_hi = (uint16_t*)take(d * L.ldn * 2); L.wt_lo = (uint16_t*)take(d * L.ldn * 2);
         L.dz_hi = (uint16_t*)take(M * L.ldn * 2); L.dz_lo = (uint16_t*)take(M * L.ldn * 2);
-        L.dzt_hi = (uint16_t*)take(N * L.ldm * 2); L.dzt_lo = (uint16_t*)take(N * L.ldm * 2);
+        int64_t f = (int64_t)L.ks_dh * M * d;
+        if ((int64_t)L.ks_dw * N * d > f) f = (int64_t)L.ks_dw * N * d;
+        if (ceil_div(M, kDbChunk) * N > f) f = ceil_div(M, kDbChunk) * N;
+        L.slabs = (float*)take(f * 4);
     }
     L.bytes = p - (char*)ws;
     return L;
 }
-
-constexpr int kBN1 = 128, kStages1 = 3;     // logits GEMM (epilogue-heavy)
-constexpr int kBN2 = 256, kStages2 = 2;     // gradient GEMMs: one tile spans d = 256 so dZ is read once
 
 }  // namespace c2dsr
 
@@ -305,10 +280,15 @@ using namespace c2dsr;
         if (rc_) return rc_;   \
     } while (0)
 
+static unsigned ew_grid(int64_t n) {
+    const int64_t b = ceil_div(n, 256);
+    return (unsigned)(b < 2368 ? (b > 0 ? b : 1) : 2368);
+}
+
 extern "C" {
 
 int64_t c2dsr_score_ce_tc_workspace_bytes(int64_t M, int64_t N, int d, int backward) {
-    return ce_layout(nullptr, M, N, d, kBN1, backward != 0).bytes + 1024;
+    return ce_layout(nullptr, M, N, d, backward != 0).bytes + 1024;
 }
 
 int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
@@ -323,20 +303,20 @@ int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, con
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const CeLayout L = ce_layout(workspace, M, N, d, kBN1, false);
+    const CeLayout L = ce_layout(workspace, M, N, d, false);
     const bool split = passes == 3;
     RUN(split_rows(H, M, d, d, L.h_hi, split ? L.h_lo : nullptr, st));
     RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
     tc::Maps maps;
     RUN(make_maps<kBN1>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
     tc::Problem pb{M, N, d, passes, 0, 1};
-    LseEpilogue epi{bias, gt, L.pmax, L.psum, L.zgt, M, N, L.n_blocks, 0.f, 0.f, 0, 0};
+    LseEpilogue epi{bias, gt, L.pmax, L.psum, L.zgt, M, N, L.n_pairs, 0.f, 0.f, 0, 0};
     if (d <= tc::ARES_MAX_KB * tc::BK) {     // the H row block stays resident in shared memory
-        RUN((launch_gemm<kBN1, kStages1, true>(maps, pb, epi, st)));
+        RUN((launch_gemm<kBN1, kStages1, true, false, false>(maps, pb, epi, st)));
     } else {
-        RUN((launch_gemm<kBN1, kStages1, false>(maps, pb, epi, st)));
+        RUN((launch_gemm<kBN1, kStages1, false, false, false>(maps, pb, epi, st)));
     }
-    lse_combine_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(L.pmax, L.psum, L.zgt, zpad, gt, M, N, L.n_blocks, lse,
+    lse_combine_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(L.pmax, L.psum, L.zgt, zpad, gt, M, N, L.n_pairs, lse,
                                                                  loss_row);
     note_launches(1);
     return check_launch("score_ce_fwd_tc");
@@ -355,52 +335,52 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const float* bias, con
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const CeLayout L = ce_layout(workspace, M, N, d, kBN1, true);
+    const CeLayout L = ce_layout(workspace, M, N, d, true);
     const bool split = passes == 3;
+    uint16_t* dz_lo = split ? L.dz_lo : nullptr;
     RUN(split_rows(H, M, d, d, L.h_hi, split ? L.h_lo : nullptr, st));
     RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
-    RUN(split_rows_transposed(H, M, d, L.ldm, L.ht_hi, split ? L.ht_lo : nullptr, st));
-    RUN(split_rows_transposed(W, N, d, L.ldn, L.wt_hi, split ? L.wt_lo : nullptr, st));
-    // 1. recompute the logits, emit dZ (both orientations)
+    // 1. recompute the logits, emit dZ [M, N] as bf16 hi / lo
     {
         tc::Maps maps;
         RUN(make_maps<kBN1>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
         tc::Problem pb{M, N, d, passes, 0, 1};
-        GradEpilogue epi{bias, gt, lse, coef, L.dz_hi, split ? L.dz_lo : nullptr, L.dzt_hi, split ? L.dzt_lo : nullptr,
-                         M, N, L.ldn, L.ldm, 0.f, 0.f, 0};
+        GradEpilogue epi{bias, gt, lse, coef, L.dz_hi, dz_lo, M, N, L.ldn, 0.f, 0.f, 0};
         if (d <= tc::ARES_MAX_KB * tc::BK) {
-            RUN((launch_gemm<kBN1, kStages1, true>(maps, pb, epi, st)));
+            RUN((launch_gemm<kBN1, kStages1, true, false, false>(maps, pb, epi, st)));
         } else {
-            RUN((launch_gemm<kBN1, kStages1, false>(maps, pb, epi, st)));
+            RUN((launch_gemm<kBN1, kStages1, false, false, false>(maps, pb, epi, st)));
         }
     }
-    // 2. dH[M, d] = dZ[M, N] * W[N, d]      (A = dZ, B = W^T, K = N)
+    // 2. dH[M, d] = dZ[M, N] W[N, d]: A = dZ (K-major, K = N), B = W read MN-major from its [N, d] storage
     {
         tc::Maps maps;
-        RUN(make_maps<kBN2>(&maps, L.dz_hi, L.dz_lo, M, L.ldn, L.wt_hi, L.wt_lo, d, L.ldn, N, passes));
+        RUN(make_maps<kBN2>(&maps, L.dz_hi, L.dz_lo, M, L.ldn, L.w_hi, L.w_lo, d, d, N, passes, false, true));
         tc::Problem pb{M, d, (int)N, passes, 0, L.ks_dh};
-        StoreEpilogue epi{L.slabs, d, M, d, 0, M * (int64_t)d, nullptr};
-        RUN((launch_gemm<kBN2, kStages2, false>(maps, pb, epi, st)));
-        const int64_t n = M * (int64_t)d;
-        slab_reduce_kernel<<<(unsigned)(ceil_div(n, 256) < 2368 ? ceil_div(n, 256) : 2368), 256, 0, st>>>(
-            L.slabs, L.ks_dh, n, dH, 0);
+        SlabEpilogue epi{L.slabs, M, d, M * (int64_t)d, nullptr};
+        RUN((launch_gemm<kBN2, kStages2, false, false, true>(maps, pb, epi, st)));
+        slab_reduce_kernel<<<ew_grid(M * (int64_t)d), 256, 0, st>>>(L.slabs, L.ks_dh, M * (int64_t)d, dH, 0);
         note_launches(1);
     }
-    // 3. dW[N, d] += dZ^T[N, M] * H[M, d]   (A = dZ^T, B = H^T, K = M)
+    // 3. dW[N, d] += dZ^T H: A = dZ read MN-major ([M, N] storage, K = M), B = H read MN-major ([M, d] storage)
     {
         tc::Maps maps;
-        RUN(make_maps<kBN2>(&maps, L.dzt_hi, L.dzt_lo, N, L.ldm, L.ht_hi, L.ht_lo, d, L.ldm, M, passes));
+        RUN(make_maps<kBN2>(&maps, L.dz_hi, L.dz_lo, N, L.ldn, L.h_hi, L.h_lo, d, d, M, passes, true, true));
         tc::Problem pb{N, d, (int)M, passes, 0, L.ks_dw};
-        StoreEpilogue epi{L.slabs, d, N, d, 0, N * (int64_t)d, nullptr};
-        RUN((launch_gemm<kBN2, kStages2, false>(maps, pb, epi, st)));
-        const int64_t n = N * (int64_t)d;
-        slab_reduce_kernel<<<(unsigned)(ceil_div(n, 256) < 2368 ? ceil_div(n, 256) : 2368), 256, 0, st>>>(
-            L.slabs, L.ks_dw, n, dW, 1);
+        SlabEpilogue epi{L.slabs, N, d, N * (int64_t)d, nullptr};
+        RUN((launch_gemm<kBN2, kStages2, false, true, true>(maps, pb, epi, st)));
+        slab_reduce_kernel<<<ew_grid(N * (int64_t)d), 256, 0, st>>>(L.slabs, L.ks_dw, N * (int64_t)d, dW, 1);
         note_launches(1);
     }
-    rowsum_bf16_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(L.dzt_hi, split ? L.dzt_lo : nullptr, N, M, L.ldm, dbias);
-    dzpad_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(zpad, lse, coef, gt, M, N, dzpad);
-    note_launches(2);
+    // 4. db[N] += column sums of dZ; dzpad
+    {
+        const int64_t n_chunks = ceil_div(M, kDbChunk);
+        dz_colsum_partial_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)n_chunks), 256, 0, st>>>(
+            L.dz_hi, dz_lo, M, N, L.ldn, L.slabs);
+        dz_colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(L.slabs, n_chunks, N, dbias);
+        dzpad_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(zpad, lse, coef, gt, M, N, dzpad);
+        note_launches(3);
+    }
     return check_launch("score_ce_bwd_tc");
 }
 

@@ -190,8 +190,8 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
     tc::Problem pb{n_q, n_q, d, passes, 1, 1};
     DiagEpilogue epi{bias_gt, s_gt, n_q};
-    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true>(maps, pb, epi, st);
-    return launch_gemm<kBN, kStages, false>(maps, pb, epi, st);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, st);
+    return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, st);
 }
 
 int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
@@ -209,8 +209,8 @@ int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint1
     tc::Problem pb{n_q, n, d, passes, 0, 1};
     CountEpilogue epi{bias, s_gt, gt, counts, S_debug, lds, n_q, n, n0, 0.f, 0, 0};
     // the queries' row block stays resident in shared memory when it fits (d <= 256); same MMA sequence either way
-    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true>(maps, pb, epi, (cudaStream_t)stream);
-    return launch_gemm<kBN, kStages, false>(maps, pb, epi, (cudaStream_t)stream);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, (cudaStream_t)stream);
+    return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -124,20 +124,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte swizzled operand tile (rows of 64 bf16): start address, SBO = 8 rows * 128 B,
-// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  The tile base must be 1024-B aligned.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+// 128-byte swizzled operand tiles, both built from 128-byte smem rows (tile base 1024-B aligned):
+//   K-major   row = one M/N index, 64 consecutive K elements inside the row (TMA box 64 k x rows).
+//             8 rows form a swizzle atom: SBO = 1024 B; LBO unused; the next UMMA_K = 16 elements are +32 B.
+//   MN-major  row = one K index, 64 consecutive M/N elements inside the row (TMA box 64 mn x 64 k = 8 KB);
+//             8 K rows form an atom: SBO = 1024 B between 8-row K groups, LBO = 8192 B between 64-wide M/N
+//             groups (one TMA box each); the next UMMA_K = 16 K rows are +2048 B.
+// Descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+constexpr int MN_GROUP_BYTES = BK * 128;     // one [64 k][64 mn] box
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, bool mn_major) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;                 // leading byte offset: unused for swizzled K-major (canonical value 1)
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                 // descriptor version
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)(mn_major ? (MN_GROUP_BYTES >> 4) : 1) << 16;     // leading byte offset
+    d |= (uint64_t)(1024 >> 4) << 32;                               // stride byte offset
+    d |= (uint64_t)1 << 46;                                         // descriptor version
+    d |= (uint64_t)2 << 61;                                         // SWIZZLE_128B
     return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// descriptor increment (in 16-byte units) for the next UMMA_K slice of a k-block
+__host__ __device__ constexpr uint32_t kstep_units(bool mn_major) { return mn_major ? (2 * 1024) >> 4 : (UMMA_K * 2) >> 4; }
+// kind::f16 instruction descriptor: D fp32, A/B bf16, M = 128, N = n; bit 15 / 16 = A / B is MN-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct Maps {
@@ -169,10 +178,31 @@ struct SmemLayout {
 //   void chunk(int64_t row, int64_t col0, const float (&v)[32]);   // columns col0..col0+31 of the tile
 //   void tile_end(int64_t row);
 // Each row of a tile is shared by EPI_PARTS threads (`part` = which BN / EPI_PARTS column range they own).
-template <int BN, int STAGES, bool ARES, class Epilogue>
+// A_MN / B_MN: the operand is MN-major (its global matrix is [K, M or N] row-major) instead of K-major.
+template <int BN, int STAGES, bool ARES, bool A_MN, bool B_MN, class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
+    static_assert(!(ARES && A_MN), "the resident-A mode is K-major only");
     using L = SmemLayout<BN, STAGES, ARES>;
+    // operand tile loaders: K-major = one box of [rows][64 k]; MN-major = one [64 k][64 mn] box per 64 rows
+    auto load_a = [&](const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int kb, int64_t m_blk) {
+        if (A_MN) {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g)
+                tma_load_2d(map, bar, dst + g * MN_GROUP_BYTES, (int)(m_blk * BM) + 64 * g, kb * BK);
+        } else {
+            tma_load_2d(map, bar, dst, kb * BK, (int)(m_blk * BM));
+        }
+    };
+    auto load_b = [&](const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int kb, int64_t n_blk) {
+        if (B_MN) {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+                tma_load_2d(map, bar, dst + g * MN_GROUP_BYTES, (int)(n_blk * BN) + 64 * g, kb * BK);
+        } else {
+            tma_load_2d(map, bar, dst, kb * BK, (int)(n_blk * BN));
+        }
+    };
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* ring = smem + L::RING_OFF;
@@ -253,8 +283,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
                 mbar_wait(a_empty, a_phase ^ 1);              // MMAs of the previous row block are done
                 mbar_arrive_expect_tx(a_full, (uint32_t)n_kb_total * (uint32_t)L::A_TILE * (split ? 2u : 1u));
                 for (int kb = 0; kb < n_kb_total; ++kb) {
-                    tma_load_2d(&maps.a_hi, a_full, smem + kb * 2 * L::A_TILE, kb * BK, (int)(m_blk * BM));
-                    if (split) tma_load_2d(&maps.a_lo, a_full, smem + kb * 2 * L::A_TILE + L::A_TILE, kb * BK, (int)(m_blk * BM));
+                    load_a(&maps.a_hi, a_full, smem + kb * 2 * L::A_TILE, kb, m_blk);
+                    if (split) load_a(&maps.a_lo, a_full, smem + kb * 2 * L::A_TILE + L::A_TILE, kb, m_blk);
                 }
                 a_phase ^= 1;
                 cur_m = m_blk;
@@ -264,11 +294,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
                 uint8_t* st = ring + stage * L::STAGE;
                 mbar_arrive_expect_tx(&full[stage], stage_bytes);
                 if (!ARES) {
-                    tma_load_2d(&maps.a_hi, &full[stage], st, kb * BK, (int)(m_blk * BM));
-                    if (split) tma_load_2d(&maps.a_lo, &full[stage], st + L::A_TILE, kb * BK, (int)(m_blk * BM));
+                    load_a(&maps.a_hi, &full[stage], st, kb, m_blk);
+                    if (split) load_a(&maps.a_lo, &full[stage], st + L::A_TILE, kb, m_blk);
                 }
-                tma_load_2d(&maps.b_hi, &full[stage], st + L::B_OFF, kb * BK, (int)(n_blk * BN));
-                if (split) tma_load_2d(&maps.b_lo, &full[stage], st + L::B_OFF + L::B_TILE, kb * BK, (int)(n_blk * BN));
+                load_b(&maps.b_hi, &full[stage], st + L::B_OFF, kb, n_blk);
+                if (split) load_b(&maps.b_lo, &full[stage], st + L::B_OFF + L::B_TILE, kb, n_blk);
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
@@ -277,7 +307,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         }
     } else if (warp == 1 && lane == 0) {
         // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc = make_idesc_bf16(BN);
+        constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
+        constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         int64_t cur_m = -1;
@@ -300,22 +331,22 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
                 tcgen05_fence_after();
                 const uint32_t st = smem_u32(ring + stage * L::STAGE);
                 const uint32_t a_base = ARES ? smem_u32(smem + kb * 2 * L::A_TILE) : st;
-                const uint64_t a_hi = make_smem_desc(a_base), a_lo = make_smem_desc(a_base + L::A_TILE);
-                const uint64_t b_hi = make_smem_desc(st + L::B_OFF);
-                const uint64_t b_lo = make_smem_desc(st + L::B_OFF + L::B_TILE);
+                const uint64_t a_hi = make_smem_desc(a_base, A_MN), a_lo = make_smem_desc(a_base + L::A_TILE, A_MN);
+                const uint64_t b_hi = make_smem_desc(st + L::B_OFF, B_MN);
+                const uint64_t b_lo = make_smem_desc(st + L::B_OFF + L::B_TILE, B_MN);
                 uint32_t accum = kb > kb0 ? 1u : 0u;
                 if (split) {      // small cross terms first, then the leading product
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, accum);
+                        umma_bf16(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, accum);
                         accum = 1u;
                     }
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
                 }
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, accum);
+                    umma_bf16(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, accum);
                     accum = 1u;
                 }
                 umma_commit(&empty[stage]);          // smem stage is free once these MMAs retire

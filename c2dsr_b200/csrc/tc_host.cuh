@@ -48,17 +48,34 @@ static inline int make_bf16_map(CUtensorMap* map, const void* base, int64_t rows
     return C2DSR_OK;
 }
 
-// maps for A [M, K] (lda) and B [N, K] (ldb), hi and (optionally) lo parts
+// One operand with `rows` M/N indices and inner extent K.  K-major: the matrix is [rows, K] (ld), one box of
+// 64 k x box_rows.  MN-major: the matrix is [K, rows] (ld), boxes of 64 mn x 64 k.
+static inline int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld,
+                                   bool mn_major, int box_rows) {
+    if (mn_major) return make_bf16_map(map, base, K, rows, ld, tc::BK);
+    return make_bf16_map(map, base, rows, K, ld, box_rows);
+}
+
+// maps for A (M rows) and B (N rows), hi and (optionally) lo parts
 template <int BN>
 static inline int make_maps(tc::Maps* maps, const uint16_t* a_hi, const uint16_t* a_lo, int64_t M, int64_t lda,
                             const uint16_t* b_hi, const uint16_t* b_lo, int64_t N, int64_t ldb, int64_t K,
-                            int passes) {
+                            int passes, bool a_mn = false, bool b_mn = false) {
     int rc;
-    if ((rc = make_bf16_map(&maps->a_hi, a_hi, M, K, lda, tc::BM))) return rc;
-    if ((rc = make_bf16_map(&maps->b_hi, b_hi, N, K, ldb, BN))) return rc;
-    if ((rc = make_bf16_map(&maps->a_lo, passes == 3 ? a_lo : a_hi, M, K, lda, tc::BM))) return rc;
-    if ((rc = make_bf16_map(&maps->b_lo, passes == 3 ? b_lo : b_hi, N, K, ldb, BN))) return rc;
+    if ((rc = make_operand_map(&maps->a_hi, a_hi, M, K, lda, a_mn, tc::BM))) return rc;
+    if ((rc = make_operand_map(&maps->b_hi, b_hi, N, K, ldb, b_mn, BN))) return rc;
+    if ((rc = make_operand_map(&maps->a_lo, passes == 3 ? a_lo : a_hi, M, K, lda, a_mn, tc::BM))) return rc;
+    if ((rc = make_operand_map(&maps->b_lo, passes == 3 ? b_lo : b_hi, N, K, ldb, b_mn, BN))) return rc;
     return C2DSR_OK;
+}
+
+// The kernel gives every K slab ceil(n_kb / slabs) k-blocks; shrink the slab count so that none is empty.
+static inline int effective_splits(int64_t K, int64_t slabs) {
+    const int64_t n_kb = ceil_div(K, tc::BK);
+    if (slabs < 1) slabs = 1;
+    if (slabs > n_kb) slabs = n_kb;
+    const int64_t per = ceil_div(n_kb, slabs);
+    return (int)ceil_div(n_kb, per);
 }
 
 static inline int sm_count() {
@@ -72,10 +89,10 @@ static inline int sm_count() {
     return n;
 }
 
-template <int BN, int STAGES, bool ARES, class Epi>
+template <int BN, int STAGES, bool ARES, bool A_MN, bool B_MN, class Epi>
 static inline int launch_gemm(const tc::Maps& maps, const tc::Problem& pb, const Epi& epi, cudaStream_t st) {
     using L = tc::SmemLayout<BN, STAGES, ARES>;
-    auto kern = tc::gemm_kernel<BN, STAGES, ARES, Epi>;
+    auto kern = tc::gemm_kernel<BN, STAGES, ARES, A_MN, B_MN, Epi>;
     if (ARES && pb.K > tc::ARES_MAX_KB * tc::BK) {
         set_error("resident-A GEMM needs K <= %d", tc::ARES_MAX_KB * tc::BK);
         return C2DSR_ERR_ARG;

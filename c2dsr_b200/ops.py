@@ -126,7 +126,8 @@ class EncoderFn(torch.autograd.Function):
     order of _LAYER_FIELDS, then the final LayerNorm weight and bias."""
 
     @staticmethod
-    def forward(ctx, x, seq, n_head: int, pad_idx: int, norm_first: bool, p: float, seed: int, tag: int, *weights):
+    def forward(ctx, x, seq, n_head: int, pad_idx: int, norm_first: bool, p: float, seed: int, tag: int,
+                dense_passes: int, *weights):
         x = _f(x)
         seq = seq.contiguous()
         n_seq, L, d = x.shape
@@ -135,28 +136,28 @@ class EncoderFn(torch.autograd.Function):
         T = n_seq * L
         saved = torch.empty(query("c2dsr_encoder_saved_floats", T, d, n_head, n_layers), device=x.device, dtype=F32)
         out = torch.empty_like(x)
-        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head), x.device)
+        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head, dense_passes), x.device)
         table = _layer_table(w, n_layers)
         call("c2dsr_encoder_fwd", C.addressof(table), n_layers, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), n_seq,
-             L, d, n_head, pad_idx, int(norm_first), LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws), ws.numel(),
-             stream())
+             L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws),
+             ws.numel(), stream())
         ctx.save_for_backward(saved, seq, *w)
-        ctx.cfg = (n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers)
+        ctx.cfg = (n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers, dense_passes)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         saved, seq, *w = ctx.saved_tensors
-        n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers = ctx.cfg
+        n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers, dense_passes = ctx.cfg
         d_out = _f(d_out)
         grads = [torch.zeros_like(t) for t in w]
         dx = torch.empty(n_seq, L, d, device=d_out.device, dtype=F32)
-        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", n_seq * L, d, n_head), d_out.device)
+        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", n_seq * L, d, n_head, dense_passes), d_out.device)
         wt, gt = _layer_table(w, n_layers), _layer_table(grads, n_layers)
         call("c2dsr_encoder_bwd", C.addressof(wt), C.addressof(gt), n_layers, ptr(w[-2]), ptr(grads[-2]),
-             ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), LN_EPS, p, seed,
-             tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
-        return (dx, None, None, None, None, None, None, None, *grads)
+             ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS,
+             p, seed, tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
+        return (dx, None, None, None, None, None, None, None, None, *grads)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -260,6 +261,14 @@ class ScoreCEFn(torch.autograd.Function):
         dbpad = torch.empty(1, device=dev, dtype=F32)
         call("c2dsr_wsum", ptr(dzpad), None, M, ptr(dbpad), stream())
         return dH, dHpad, dW, db, dwpad, dbpad, None, None
+
+
+def gemm_tc(ta, tb, M, N, K, A, lda, B, ldb, Cm, ldc, beta=0.0, bias=None, act=0, passes=3):
+    """C = act(op(A) op(B) + bias) + beta C on the tcgen05 path (same operand conventions as gemm())."""
+    ws = workspace.get(query("c2dsr_gemm_tc_workspace_bytes", M, N, K), Cm.device)
+    call("c2dsr_gemm_tc", ta, tb, M, N, K, ptr(A), lda, ptr(B), ldb, beta, ptr(Cm), ldc, ptr(bias), act, 0.0, 0, 0,
+         passes, ptr(ws), ws.numel(), stream())
+    return Cm
 
 
 class ScoreCETcFn(torch.autograd.Function):

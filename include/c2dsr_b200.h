@@ -75,6 +75,14 @@ int64_t c2dsr_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int c2dsr_gemm(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, const float* A, int64_t lda,
                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act,
                float p, uint64_t seed, uint64_t tag, void* workspace, int64_t workspace_bytes, void* stream);
+/* Same product on tensor cores (tcgen05 + TMA + tensor memory): operands are split into bf16 hi / lo
+ * (passes = 3: hi*hi + hi*lo + lo*hi, fp32-grade; passes = 1: hi only) and accumulated in fp32.
+ * Transposed operands (ta = 1, tb = 0) are read MN-major from their row-major storage.  alpha is 1,
+ * beta must be 0 or 1.  Short grids with a long K are cut into K slabs added in a fixed order. */
+int64_t c2dsr_gemm_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int c2dsr_gemm_tc(int ta, int tb, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, float beta, float* C, int64_t ldc, const float* bias, int act, float p, uint64_t seed,
+                  uint64_t tag, int passes, void* workspace, int64_t workspace_bytes, void* stream);
 /* out[N] (+)= sum over rows of X[M,N] (ldx), fixed summation order.  With a workspace of at least
  * ceil(M/128) * N floats the reduction runs in two phases over a 2-D grid. */
 int c2dsr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* workspace,
@@ -99,18 +107,19 @@ typedef struct {
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
 } c2dsr_layer_grads;
 
-/* floats the forward saves for the backward (`saved`), and scratch bytes for either pass */
+/* floats the forward saves for the backward (`saved`), and scratch bytes for either pass.
+ * dense_passes selects the kernels of the dense layers: 0 = fp32 FFMA, 3 / 1 = tcgen05 (bf16 hi/lo split / bf16). */
 int64_t c2dsr_encoder_saved_floats(int64_t n_tok, int d, int n_head, int n_layers);
-int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head);
+int64_t c2dsr_encoder_workspace_bytes(int64_t n_tok, int d, int n_head, int dense_passes);
 int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers_host, int n_layers, const float* lnf_w, const float* lnf_b,
                       const float* x, const int64_t* seq, int64_t n_seq, int L, int d, int n_head, int64_t pad_idx,
-                      int norm_first, float eps, float p, uint64_t seed, uint64_t tag, float* out, float* saved,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      int norm_first, int dense_passes, float eps, float p, uint64_t seed, uint64_t tag, float* out,
+                      float* saved, void* workspace, int64_t workspace_bytes, void* stream);
 /* Gradients are ACCUMULATED (+=) into `grads` and lnf grads; dx is overwritten. */
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers_host, const c2dsr_layer_grads* grads_host, int n_layers,
                       const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,
-                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, float eps, float p,
-                      uint64_t seed, uint64_t tag, const float* saved, float* dx, void* workspace,
+                      int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first, int dense_passes,
+                      float eps, float p, uint64_t seed, uint64_t tag, const float* saved, float* dx, void* workspace,
                       int64_t workspace_bytes, void* stream);
 
 /* primitives of the encoder, exported for unit tests */

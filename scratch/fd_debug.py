@@ -22,7 +22,7 @@ for eps in (1e-2, 4e-3, 1e-3, 1e-4):
 wl = [t.to(DEV) for t in _weight_list(W, nl)]
 for p in (0.0, 0.3):
     xg = x.to(DEV).requires_grad_(True)
-    out = ops.EncoderFn.apply(xg, seq.to(DEV), H, pad, False, p, 1234, 5, *wl)
+    out = ops.EncoderFn.apply(xg, seq.to(DEV), H, pad, False, p, 1234, 5, 3, *wl)
     (out * c.to(DEV)).sum().backward()
     an = float((xg.grad.double() * v.to(DEV).double()).sum())
     f = lambda xx: float((ops.EncoderFn.apply(xx, seq.to(DEV), H, pad, False, p, 1234, 5, *wl).double() * c.to(DEV).double()).sum())

@@ -227,7 +227,8 @@ def _weight_list(W, n_layers):
 
 @pytest.mark.parametrize("B,L,d,H,n_layers,norm_first", [(48, 15, 256, 1, 1, False), (20, 10, 32, 2, 2, False),
                                                          (20, 10, 32, 4, 2, True), (6, 50, 128, 2, 1, False)])
-def test_encoder_fwd_bwd_vs_oracle(B, L, d, H, n_layers, norm_first):
+@pytest.mark.parametrize("dense", [0, 3])
+def test_encoder_fwd_bwd_vs_oracle(B, L, d, H, n_layers, norm_first, dense):
     """Includes rows with no pad at all (fully masked queries -> attention output 0)."""
     ops, _ = _ops()
     g = torch.Generator().manual_seed(B * L + d + H)
@@ -242,13 +243,16 @@ def test_encoder_fwd_bwd_vs_oracle(B, L, d, H, n_layers, norm_first):
     ref.backward(go)
     wl = [t.to(DEV).requires_grad_(True) for t in _weight_list(W, n_layers)]
     xg = x.to(DEV).requires_grad_(True)
-    out = ops.EncoderFn.apply(xg, seq.to(DEV), H, pad, norm_first, 0.0, 0, 0, *wl)
+    out = ops.EncoderFn.apply(xg, seq.to(DEV), H, pad, norm_first, 0.0, 0, 0, dense, *wl)
     assert rel_err(out.detach().cpu(), ref.detach()) < 2e-5
     out.backward(go.to(DEV))
-    assert rel_err(xg.grad.cpu(), xc.grad) < 1e-4
+    # tensor-core dense layers (bf16 hi/lo split, ~1e-5 on pre-activations) flip a handful of ReLU units
+    # per batch: the element-wise bound is looser there, the fp32 FFMA layers must match to 1e-4
+    tol = 1e-4 if dense == 0 else 5e-3
+    assert rel_err(xg.grad.cpu(), xc.grad) < tol
     for got, ref_t in zip(wl, _weight_list(Wc, n_layers)):
         scale = float(ref_t.grad.abs().max())
-        assert float((got.grad.cpu() - ref_t.grad).abs().max()) <= 1e-4 * scale + 1e-6
+        assert float((got.grad.cpu() - ref_t.grad).abs().max()) <= tol * scale + 1e-6
 
 
 @pytest.mark.parametrize("p", [0.0, 0.3])
@@ -264,8 +268,8 @@ def test_encoder_dropout_gradient_is_consistent(p):
     wl = [t.to(DEV) for t in _weight_list(_encoder_weights(d, nl, g), nl)]
     c = torch.randn(B, L, d, generator=g).to(DEV)
     v = torch.randn(B, L, d, generator=g).to(DEV)
-    f = lambda xx: float((ops.EncoderFn.apply(xx, seq, H, pad, False, p, 1234, 5, *wl).double() * c.double()).sum())
-    out = ops.EncoderFn.apply(x, seq, H, pad, False, p, 1234, 5, *wl)
+    f = lambda xx: float((ops.EncoderFn.apply(xx, seq, H, pad, False, p, 1234, 5, 3, *wl).double() * c.double()).sum())
+    out = ops.EncoderFn.apply(x, seq, H, pad, False, p, 1234, 5, 3, *wl)
     (out * c).sum().backward()
     analytic = float((x.grad.double() * v.double()).sum())
     errs = []
@@ -276,7 +280,7 @@ def test_encoder_dropout_gradient_is_consistent(p):
         errs.append(abs(analytic - numeric) - 0.03 * abs(numeric) - 0.15)
     assert min(errs) <= 0, (analytic, errs)
     if p > 0:                                                        # and dropout really is on
-        out0 = ops.EncoderFn.apply(x.detach(), seq, H, pad, False, 0.0, 1234, 5, *wl)
+        out0 = ops.EncoderFn.apply(x.detach(), seq, H, pad, False, 0.0, 1234, 5, 3, *wl)
         assert rel_err(out.detach().cpu(), out0.cpu()) > 1e-2
 
 

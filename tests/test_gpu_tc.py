@@ -105,3 +105,21 @@ def test_score_ce_tc_vs_oracle(M, N, d, passes):
     for got, r, nm in zip(dl, leaves, ("dH", "dHpad", "dW", "db", "dwpad", "dbpad")):
         err = float((got.grad.cpu().double() - r.grad).abs().max()) / float(r.grad.abs().max())
         assert err < tol_g, (nm, err)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 1), (0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 136), (768, 256, 11520), (3840, 768, 256), (130, 70, 40)])
+def test_gemm_tc_all_layouts(ta, tb, M, N, K):
+    """tcgen05 GEMM with K-major and MN-major operands (transposed operands are read in place) vs fp64."""
+    from c2dsr_b200 import ops
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K + ta * 2 + tb)
+    A = torch.randn((K, M) if ta else (M, K), generator=g)
+    B = torch.randn((N, K) if tb else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    opA, opB = (A.t() if ta else A).double(), (B.t() if tb else B).double()
+    ref = torch.relu(opA @ opB + bias.double()) + C0.double()
+    Cd = C0.to(DEV).clone()
+    ops.gemm_tc(ta, tb, M, N, K, A.to(DEV), A.shape[1], B.to(DEV), B.shape[1], Cd, N, beta=1.0, bias=bias.to(DEV), act=1)
+    err = float((Cd.cpu().double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-5, err
