@@ -43,6 +43,9 @@ class SelfAttention(nn.Module):
         # perturbation of a pre-activation flips a handful of units per batch, which shows up as O(1e-3)
         # element-wise gradient differences although the loss is unaffected.
         self.dense_passes = int(getattr(args, "encoder_tc_passes", 0))
+        # without autograd (evaluation) the ReLU is only evaluated, never differentiated, and it is continuous:
+        # the tensor-core path (3-pass split, ~1e-5) is used whenever the score path is the tensor-core one
+        self.dense_passes_eval = int(getattr(args, "tc_passes", 3)) if getattr(args, "score_path", "tc") == "tc" else 0
         self.register_buffer("attn_mask", nn.Transformer.generate_square_subsequent_mask(args.len_max))
         self.dropout_attn = nn.Dropout(p=args.dropout_attn)
         self.pos_emb = nn.Embedding(args.len_max, args.d_latent)
@@ -65,8 +68,9 @@ class SelfAttention(nn.Module):
     def encode(self, seq, x, seed: int, tag: int):
         """x already holds sqrt(d) * (hi[seq] + E[seq]) + P[pos] with input dropout applied."""
         p = self.p if self.training else 0.0
-        return ops.EncoderFn.apply(x, seq, self.n_head, self.idx_pad, self.norm_first, p, seed, tag,
-                                   self.dense_passes, *self.weights())
+        dense = self.dense_passes if (torch.is_grad_enabled() and x.requires_grad) else self.dense_passes_eval
+        return ops.EncoderFn.apply(x, seq, self.n_head, self.idx_pad, self.norm_first, p, seed, tag, dense,
+                                   *self.weights())
 
 
 class C2DSR(nn.Module):

@@ -429,17 +429,201 @@ static AttnShape make_shape(int64_t n_seq, int L, int d, int H, int64_t pad) {
     AttnShape sh{n_seq, L, d, H, d / H, pad, 1.f / sqrtf((float)(d / H))};
     return sh;
 }
+// ---- one CTA per (sequence, head): Q, K, V (and dO, O) staged in shared memory ------------------------------
+// Short sequences (L * head_dim * 5 floats <= 160 KB) take this path: every global element is read once,
+// coalesced; all dot products run out of shared memory; sums over keys / queries have a fixed order.
+constexpr int kSeqThreads = 128;
+constexpr int kSeqSmemLimit = 160 * 1024;
+
+__device__ __forceinline__ float smem_dot(const float* a, const float* b, int dh, int lane) {
+    float s = 0.f;
+    for (int e = lane; e < dh; e += 32) s += a[e] * b[e];
+    return warp_sum(s);
+}
+
+__global__ void __launch_bounds__(kSeqThreads)
+attn_seq_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ seq, AttnShape sh, Dropout dr,
+                    float* __restrict__ o, float* __restrict__ lse) {
+    extern __shared__ float sm[];
+    const int L = sh.L, dh = sh.dh;
+    float* Q = sm;
+    float* K = Q + L * dh;
+    float* V = K + L * dh;
+    int* allow = reinterpret_cast<int*>(V + L * dh);
+    const int64_t b = blockIdx.x / sh.H;
+    const int h = blockIdx.x % sh.H;
+    const int64_t ld = 3 * (int64_t)sh.d;
+    for (int idx = threadIdx.x; idx < L * dh; idx += blockDim.x) {
+        const int i = idx / dh, e = idx % dh;
+        const float* row = qkv + (b * L + i) * ld + h * dh + e;
+        Q[idx] = row[0];
+        K[idx] = row[sh.d];
+        V[idx] = row[2 * sh.d];
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) allow[j] = seq[b * L + j] == sh.pad;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nper = (dh + 31) >> 5;
+    for (int i = warp; i < L; i += nw) {
+        float acc[kMaxPerLane];
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) acc[k] = 0.f;
+        float m = -INFINITY, l = 0.f;
+        for (int j = 0; j <= i; ++j) {
+            if (!allow[j]) continue;
+            const float s = smem_dot(Q + i * dh, K + j * dh, dh, lane) * sh.scale;
+            const float m_new = fmaxf(m, s);
+            const float corr = expf(m - m_new);
+            const float pe = expf(s - m_new);
+            l = l * corr + pe;
+            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+                const int e = lane + 32 * k;
+                if (k < nper && e < dh) acc[k] = acc[k] * corr + pe * keep * V[j * dh + e];
+            }
+            m = m_new;
+        }
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        const int64_t ti = b * L + i;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < dh) o[ti * sh.d + h * dh + e] = acc[k] * inv;
+        }
+        if (lane == 0) lse[ti * sh.H + h] = l > 0.f ? m + logf(l) : INFINITY;
+    }
+}
+
+__global__ void __launch_bounds__(kSeqThreads)
+attn_seq_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
+                    const float* __restrict__ d_o, const int64_t* __restrict__ seq, AttnShape sh, Dropout dr,
+                    float* __restrict__ d_qkv) {
+    extern __shared__ float sm[];
+    const int L = sh.L, dh = sh.dh;
+    float* Q = sm;
+    float* K = Q + L * dh;
+    float* V = K + L * dh;
+    float* dO = V + L * dh;
+    float* O = dO + L * dh;
+    float* Pk = O + L * dh;            // [L][L]  p_ij * keep_ij          (for dV)
+    float* dS = Pk + L * L;            // [L][L]  dS_ij * scale           (for dK)
+    int* allow = reinterpret_cast<int*>(dS + L * L);
+    const int64_t b = blockIdx.x / sh.H;
+    const int h = blockIdx.x % sh.H;
+    const int64_t ld = 3 * (int64_t)sh.d;
+    for (int idx = threadIdx.x; idx < L * dh; idx += blockDim.x) {
+        const int i = idx / dh, e = idx % dh;
+        const int64_t t = b * L + i;
+        const float* row = qkv + t * ld + h * dh + e;
+        Q[idx] = row[0];
+        K[idx] = row[sh.d];
+        V[idx] = row[2 * sh.d];
+        dO[idx] = d_o[t * sh.d + h * dh + e];
+        O[idx] = o[t * sh.d + h * dh + e];
+    }
+    for (int j = threadIdx.x; j < L; j += blockDim.x) allow[j] = seq[b * L + j] == sh.pad;
+    for (int idx = threadIdx.x; idx < 2 * L * L; idx += blockDim.x) Pk[idx] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nper = (dh + 31) >> 5;
+    // phase 1: per query i -> dq_i, and the (i, j) coefficients
+    for (int i = warp; i < L; i += nw) {
+        float g[kMaxPerLane];
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) g[k] = 0.f;
+        const float D = smem_dot(dO + i * dh, O + i * dh, dh, lane);
+        const float lse_i = lse[(b * L + i) * sh.H + h];
+        for (int j = 0; j <= i; ++j) {
+            if (!allow[j]) continue;
+            const float s = smem_dot(Q + i * dh, K + j * dh, dh, lane) * sh.scale;
+            const float p = expf(s - lse_i);
+            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
+            const float dP = smem_dot(dO + i * dh, V + j * dh, dh, lane) * keep;
+            const float ds = p * (dP - D) * sh.scale;
+            if (lane == 0) {
+                Pk[i * L + j] = p * keep;
+                dS[i * L + j] = ds;
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxPerLane; ++k) {
+                const int e = lane + 32 * k;
+                if (k < nper && e < dh) g[k] += ds * K[j * dh + e];
+            }
+        }
+        const int64_t ti = b * L + i;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < dh) d_qkv[ti * ld + h * dh + e] = g[k];
+        }
+    }
+    __syncthreads();
+    // phase 2: per key j -> dk_j, dv_j (zero rows for keys that are never attended)
+    for (int j = warp; j < L; j += nw) {
+        float gk[kMaxPerLane], gv[kMaxPerLane];
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) gk[k] = gv[k] = 0.f;
+        if (allow[j]) {
+            for (int i = j; i < L; ++i) {
+                const float ds = dS[i * L + j], pk = Pk[i * L + j];
+#pragma unroll
+                for (int k = 0; k < kMaxPerLane; ++k) {
+                    const int e = lane + 32 * k;
+                    if (k < nper && e < dh) {
+                        gk[k] += ds * Q[i * dh + e];
+                        gv[k] += pk * dO[i * dh + e];
+                    }
+                }
+            }
+        }
+        const int64_t tj = b * L + j;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < dh) {
+                d_qkv[tj * ld + sh.d + h * dh + e] = gk[k];
+                d_qkv[tj * ld + 2 * sh.d + h * dh + e] = gv[k];
+            }
+        }
+    }
+}
+
+static int seq_smem_bytes(const AttnShape& sh, bool bwd) {
+    return ((bwd ? 5 : 3) * sh.L * sh.dh + (bwd ? 2 * sh.L * sh.L : 0) + sh.L) * 4;
+}
+
 static int launch_attn_fwd(const float* qkv, const int64_t* seq, AttnShape sh, Dropout dr, float* o, float* lse,
                            cudaStream_t st) {
-    const int64_t warps = sh.n_seq * sh.H * sh.L;
-    attn_fwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, seq, sh, dr, o, lse);
+    const int smem = seq_smem_bytes(sh, false);
+    if (smem <= kSeqSmemLimit) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(attn_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemLimit);
+            attr = true;
+        }
+        attn_seq_fwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, smem, st>>>(qkv, seq, sh, dr, o, lse);
+    } else {
+        const int64_t warps = sh.n_seq * sh.H * sh.L;
+        attn_fwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, seq, sh, dr, o, lse);
+    }
     note_launches(1);
     return check_launch("attention_fwd");
 }
 static int launch_attn_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
                            AttnShape sh, Dropout dr, float* d_qkv, cudaStream_t st) {
-    const int64_t warps = 2 * sh.n_seq * sh.H * sh.L;
-    attn_bwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+    const int smem = seq_smem_bytes(sh, true);
+    if (smem <= kSeqSmemLimit) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(attn_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemLimit);
+            attr = true;
+        }
+        attn_seq_bwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, smem, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+    } else {
+        const int64_t warps = 2 * sh.n_seq * sh.H * sh.L;
+        attn_bwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+    }
     note_launches(1);
     return check_launch("attention_bwd");
 }

@@ -25,12 +25,39 @@ struct LinearEpilogue {
         if (row >= M) return;
         if (slab_stride) {                      // raw partial sums, compact [M, N]
             float* c = base + row * N + col0;
+            if (col0 + 32 <= N && (N & 3) == 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (col0 + i < N) c[i] = v[i];
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4*>(c)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col0 + i < N) c[i] = v[i];
+            }
             return;
         }
         float* c = base + row * ldc + col0;
+        if (col0 + 32 <= N && dr.p == 0.f && (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0 &&
+            (!bias || (reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+            // interior chunk: 8 x 16-byte loads / stores per thread
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float4 x = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0) + j);
+                    x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                }
+                if (act == 1) {
+                    x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                }
+                if (beta != 0.f) {
+                    const float4 o = reinterpret_cast<const float4*>(c)[j];
+                    x.x += beta * o.x; x.y += beta * o.y; x.z += beta * o.z; x.w += beta * o.w;
+                }
+                reinterpret_cast<float4*>(c)[j] = x;
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             const int64_t n = col0 + i;
