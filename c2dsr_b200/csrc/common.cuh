@@ -34,7 +34,7 @@ static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 struct Dropout {
     float p;             // drop probability; 0 disables
     float inv_keep;      // 1 / (1 - p)
-    uint32_t thresh;     // keep iff hash32 >= thresh
+    uint32_t thresh;     // keep iff the element's 16-bit hash lane >= thresh
     uint64_t key;        // seed mixed with the call-site tag
 };
 
@@ -48,18 +48,19 @@ static inline uint64_t host_mix64(uint64_t z) {
 static inline Dropout make_dropout(float p, uint64_t seed, uint64_t tag) {
     Dropout d;
     d.p = (p > 0.f && p < 1.f) ? p : 0.f;
-    d.inv_keep = 1.f / (1.f - d.p);
-    double t = (double)d.p * 4294967296.0;
-    d.thresh = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+    double t = (double)d.p * 65536.0 + 0.5;
+    d.thresh = (uint32_t)(t > 65535.0 ? 65535.0 : t);                 // 16-bit threshold
+    d.inv_keep = (float)(1.0 / (1.0 - (double)d.thresh / 65536.0));
     d.key = host_mix64(seed ^ host_mix64(tag));
     return d;
 }
 
-// One 64-bit mix serves a PAIR of consecutive elements: element idx uses the high half of
-// mix(idx >> 1) when idx is even, the low half when odd.  All kernels use these two helpers, so the
-// mask of element idx is the same whether it is generated one element or four at a time.
-__device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t pair) {
-    uint64_t z = key + pair * 0x9E3779B97F4A7C15ull;
+// One 64-bit mix serves FOUR consecutive elements: element idx keeps iff the 16-bit lane (idx & 3) of
+// mix(idx >> 2) is >= thresh (= round(p * 65536)); 1/(1-p) is taken from the quantised p so the mask stays
+// unbiased.  All kernels use these two helpers, so the mask of element idx is the same whether it is
+// generated one element or four at a time.
+__device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t quad) {
+    uint64_t z = key + quad * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     return z ^ (z >> 31);
@@ -68,19 +69,19 @@ __device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t pair) {
 // multiplicative mask value: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_scale(const Dropout& d, uint64_t idx) {
     if (d.p == 0.f) return 1.f;
-    const uint64_t z = mix64(d.key, idx >> 1);
-    const uint32_t h = (idx & 1) ? (uint32_t)z : (uint32_t)(z >> 32);
+    const uint64_t z = mix64(d.key, idx >> 2);
+    const uint32_t h = (uint32_t)(z >> (16 * (idx & 3))) & 0xffffu;
     return h >= d.thresh ? d.inv_keep : 0.f;
 }
 
 // four consecutive elements starting at a multiple of 4
 __device__ __forceinline__ void drop_scale4(const Dropout& d, uint64_t base, float4& v) {
     if (d.p == 0.f) return;
-    const uint64_t z0 = mix64(d.key, base >> 1), z1 = mix64(d.key, (base >> 1) + 1);
-    v.x *= (uint32_t)(z0 >> 32) >= d.thresh ? d.inv_keep : 0.f;
-    v.y *= (uint32_t)z0 >= d.thresh ? d.inv_keep : 0.f;
-    v.z *= (uint32_t)(z1 >> 32) >= d.thresh ? d.inv_keep : 0.f;
-    v.w *= (uint32_t)z1 >= d.thresh ? d.inv_keep : 0.f;
+    const uint64_t z = mix64(d.key, base >> 2);
+    v.x *= ((uint32_t)z & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
+    v.y *= ((uint32_t)(z >> 16) & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
+    v.z *= ((uint32_t)(z >> 32) & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
+    v.w *= (uint32_t)(z >> 48) >= d.thresh ? d.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -76,19 +76,22 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int64_t row, int v
 template <int VPL>   // float4 vectors per lane: d <= 128 * VPL
 __global__ void __launch_bounds__(256) spmm_kernel(SpmmArgs a, bool skip_long) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= a.n_rows) return;
-    const int beg = a.rowptr[row], end = a.rowptr[row + 1];
-    if (skip_long && end - beg > kLongRow) return;
     const int nv = a.d >> 2;
-    float4 acc[VPL];
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // persistent warps: rows are short (a few non-zeros), so each warp walks a strided set of rows instead of
+    // paying a block launch per 8 rows
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.n_rows; row += n_warps) {
+        const int beg = a.rowptr[row], end = a.rowptr[row + 1];
+        if (skip_long && end - beg > kLongRow) continue;
+        float4 acc[VPL];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    accumulate_range<VPL>(a, beg, end, lane, nv, acc);
+        for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        accumulate_range<VPL>(a, beg, end, lane, nv, acc);
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-        const int vi = lane + 32 * k;
-        if (vi < nv) finish_row(a, row, vi, acc[k]);
+        for (int k = 0; k < VPL; ++k) {
+            const int vi = lane + 32 * k;
+            if (vi < nv) finish_row(a, row, vi, acc[k]);
+        }
     }
 }
 
@@ -137,7 +140,8 @@ extern "C" int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float
     C2DSR_REQUIRE(X != out, "spmm cannot run in place on X");
     SpmmArgs a{rowptr, col, val, X, Y, Z, out, n_rows, d, alpha, beta, gamma, drop_mode, make_dropout(p, seed, tag)};
     if (a.dr.p == 0.f) a.drop_mode = 0;
-    const unsigned blocks = (unsigned)ceil_div(n_rows, 8);
+    const int64_t want = ceil_div(n_rows, 8);
+    const unsigned blocks = (unsigned)(want < 148 * 8 ? want : 148 * 8);      // 8 resident CTAs of 8 warps per SM
     cudaStream_t st = (cudaStream_t)stream;
     const bool split = long_rows != nullptr && n_long > 0;
     const int smem = 32 * d * 4;
