@@ -125,6 +125,38 @@ __global__ void adamw_kernel(const c2dsr_adam_tensor* __restrict__ table, float 
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float decay = 1.f - lr * wd;
     const float step_size = lr * inv_bc1;   // lr / bias_correction1
+    auto update = [&](float g, float& p, float& m, float& v, float& vm) {
+        p *= decay;
+        m = m + (g - m) * (1.f - beta1);                  // torch: exp_avg.lerp_(grad, 1 - beta1)
+        v = v * beta2 + (1.f - beta2) * g * g;            // exp_avg_sq.mul_(b2).addcmul_(g, g, 1 - b2)
+        vm = fmaxf(vm, v);
+        p -= step_size * (m / (sqrtf(vm) / sqrt_bc2 + eps));
+    };
+    // 16-byte path for tensors whose arrays are all float4-aligned (every large tensor is)
+    const uintptr_t bits = (uintptr_t)t.p | (uintptr_t)t.acc | (uintptr_t)t.m | (uintptr_t)t.v | (uintptr_t)t.vmax |
+                           (uintptr_t)t.g;
+    if ((bits & 15) == 0 && (t.n & 3) == 0) {
+        const int64_t n4 = t.n >> 2;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+            float4 g = reinterpret_cast<const float4*>(t.acc)[i];
+            if (t.g) {
+                const float4 gn = reinterpret_cast<const float4*>(t.g)[i];
+                g.x += gn.x; g.y += gn.y; g.z += gn.z; g.w += gn.w;
+                reinterpret_cast<float4*>(t.acc)[i] = g;
+            }
+            float4 p = reinterpret_cast<float4*>(t.p)[i], m = reinterpret_cast<float4*>(t.m)[i];
+            float4 v = reinterpret_cast<float4*>(t.v)[i], vm = reinterpret_cast<float4*>(t.vmax)[i];
+            update(g.x, p.x, m.x, v.x, vm.x);
+            update(g.y, p.y, m.y, v.y, vm.y);
+            update(g.z, p.z, m.z, v.z, vm.z);
+            update(g.w, p.w, m.w, v.w, vm.w);
+            reinterpret_cast<float4*>(t.p)[i] = p;
+            reinterpret_cast<float4*>(t.m)[i] = m;
+            reinterpret_cast<float4*>(t.v)[i] = v;
+            reinterpret_cast<float4*>(t.vmax)[i] = vm;
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += stride) {
         float g = t.acc[i];
         if (t.g) {

@@ -83,13 +83,23 @@ __global__ void item_rows_kernel(const float* __restrict__ dx, const int64_t* __
     if (cnt[key] == 1) {
         add_row(t);
     } else {
-        for (int64_t base = t & ~(int64_t)31; base < n_tok; base += 32) {      // earlier tokens cannot match
-            const int64_t j = base + lane;
-            unsigned m = __ballot_sync(0xffffffffu, j < n_tok && j >= t && seq[j] == key);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                add_row(base + b);
+        // scan the token list from t on (earlier tokens cannot match); 8 independent 256-byte loads in flight
+        for (int64_t base = t & ~(int64_t)31; base < n_tok; base += 32 * 8) {
+            int64_t k[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t j = base + 32 * u + lane;
+                k[u] = j < n_tok ? __ldg(seq + j) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t j = base + 32 * u + lane;
+                unsigned m = __ballot_sync(0xffffffffu, j >= t && k[u] == key);
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    add_row(base + 32 * u + b);
+                }
             }
         }
     }
