@@ -1,0 +1,121 @@
+"""Other BASELINE.json configurations on the B200, at sizes the oracle finishes in seconds:
+hidden-size / sequence-length sweep corners (d up to 512, L up to 200: streaming-A tcgen05 GEMM, per-query
+attention kernels, 201-bin gather backward), the Entertainment-Education defaults through main.py on synthetic
+raw logs (use_raw preprocessing, 2 epochs, model selection, StepLR), and a 1M-item style sharded evaluation."""
+import argparse
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import helpers  # noqa: F401
+import c2dsr_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+class Quiet:
+    def log_train(self, *a):
+        pass
+
+    def log_msg(self, *a):
+        pass
+
+
+def _setup(d, L, n_head, n_attn, B, na=300, nb=700, seed=0, **over):
+    from c2dsr_b200 import synth
+    from c2dsr_b200.dataloader import BatchLoader, CDSRDataset, preprocess_evaluate, preprocess_train
+    from c2dsr_b200.graph import _to_sparse, normalised_coo, transition_edges
+    from c2dsr_b200.trainer import Trainer
+    hp = dict(data="fk", dataset="Food-Kitchen", len_rec=min(10, L), n_neg_sample=50, d_latent=d, shared_item_embed=False,
+              d_bias=False, n_gnn=1, dropout_gnn=0.0, n_attn=n_attn, n_head=n_head, dropout_attn=0.0, norm_first=False,
+              lr=1e-3, l2=5e-4, lr_gamma=0.5, lr_step=10, len_max=L, lambda_loss=0.7, seed=3407, batch_size=B,
+              batch_size_eval=64, n_item_a=na, n_item_b=nb, n_item=na + nb + 1, idx_pad=na + nb, full_catalog=True)
+    hp.update(over)
+    seqs = synth.make_sequences(4 * B, na, nb, len_max=L, seed=seed, lengths="uniform" if L > 15 else "fk")
+    seqs = [s[:L] for s in seqs]
+    sh, sp = transition_edges(seqs, na)
+    adj = (_to_sparse(normalised_coo(sh, hp["n_item"]), hp["n_item"]).coalesce(),
+           _to_sparse(normalised_coo(sp, hp["n_item"]), hp["n_item"]).coalesce())
+    random.seed(1)
+    fields = preprocess_train(seqs, na, nb, L)[:B]
+    six, four, neg = preprocess_evaluate(seqs[:64], na, nb, L, hp["n_neg_sample"])
+    args = argparse.Namespace(**hp)
+    args.device = torch.device(DEV)
+    torch.manual_seed(1)
+    ds = CDSRDataset.from_fields([fields[:, i] for i in range(14)], "train", L)
+    tr = Trainer.from_parts(args, Quiet(), (BatchLoader(ds, B), None, None), adj[0], adj[1])
+    state = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    otr = oracle.OracleTrainer(state, adj[0], adj[1], hp)
+    batch = tuple(torch.from_numpy(np.ascontiguousarray(fields[:, i])) for i in range(14))
+    ebatch = tuple(torch.from_numpy(np.ascontiguousarray(six[:, i])) for i in range(6)) + \
+        tuple(torch.from_numpy(np.ascontiguousarray(four[:, i:i + 1])) for i in range(4)) + (torch.from_numpy(neg),)
+    return tr, otr, batch, ebatch
+
+
+@pytest.mark.parametrize("d,L,n_head,n_attn,B", [(512, 15, 1, 1, 32), (128, 50, 2, 1, 24), (256, 200, 1, 1, 6),
+                                                 (512, 200, 4, 2, 4)])
+def test_sweep_corner_matches_oracle(d, L, n_head, n_attn, B):
+    tr, otr, batch, ebatch = _setup(d, L, n_head, n_attn, B)
+    tr.model.train(); tr.optimizer.zero_grad(); otr.zero_grad()
+    for step in range(2):
+        tr.model.convolve_graph()
+        got = [float(x) for x in tr.train_batch(batch)]
+        ref = [float(x) for x in otr.train_batch(batch, training=True)]
+        np.testing.assert_allclose(got, ref, rtol=1e-4)
+    tr.model.eval()
+    with torch.no_grad():
+        tr.model.convolve_graph()
+        ra, rb = tr.evaluate_batch(ebatch)
+    otr.convolve_graph()
+    oa, ob = otr.evaluate_batch(ebatch, full_catalog=True)
+    assert len(ra) == len(oa) and len(rb) == len(ob)
+    assert sum(abs(x - y) for x, y in zip(ra + rb, oa + ob)) <= 2
+
+
+def test_main_entertainment_education_defaults(tmp_path, monkeypatch):
+    """BASELINE configs[0]: the EE defaults (d=128, len_max=30, dropouts 0.2, batch 512) through main.py with
+    --use_raw on synthetic raw logs: preprocessing, graph, 2 epochs, validation, model selection, test."""
+    from c2dsr_b200 import synth
+    from c2dsr_b200.main import main
+    na, nb = 400, 1500
+    raw = tmp_path / "data" / "raw" / "Entertainment-Education"
+    for mode, n, seed in (("train", 1500, 1), ("val", 200, 2), ("test", 200, 3)):
+        seqs = synth.make_sequences(n, na, nb, len_max=29, seed=seed, lengths="full")
+        synth.write_raw(str(raw / f"{mode}_new.txt"), seqs)
+    synth.write_item_lists(str(raw), na, nb)
+    os.makedirs(tmp_path / "data" / "Entertainment-Education", exist_ok=True)
+    monkeypatch.chdir(tmp_path)
+    best, res = main(["--data", "ee", "--cuda", "0", "--use_raw", "--n_epoch", "2", "--n_neg_sample", "99"])
+    assert len(res) == 13 and all(np.isfinite(res))
+    assert 0.0 <= res[1] <= 1.0 and os.listdir(tmp_path / "log")
+
+
+def test_million_item_style_sharded_eval():
+    """BASELINE configs[3] in miniature: a 200k-item domain scored in 8 catalogue shards; partial counts add up
+    to the unsharded full-catalogue ranks (what the 8-GPU run all-reduces)."""
+    from c2dsr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n_q, N, d = 512, 200_000, 256
+    Q = torch.randn(n_q, d, generator=g).to(DEV)
+    W = (torch.randn(N, d, generator=g) * 0.02).to(DEV)
+    b = torch.zeros(N, device=DEV)
+    gt = torch.randint(0, N, (n_q,), generator=g).to(DEV)
+    full, s_full, _ = ops.score_rank_tc(Q, ops.split_bf16(W), b, gt, 0, N)
+    counts = torch.zeros(n_q, dtype=torch.int32, device=DEV)
+    s_sum = torch.zeros(n_q, device=DEV)
+    per = (N + 7) // 8
+    splits = [(ops.split_bf16(W[r * per:min((r + 1) * per, N)].contiguous()), r * per, min((r + 1) * per, N)) for r in range(8)]
+    for ws, n0, n1 in splits:
+        _, s, _ = ops.score_rank_tc(Q, ws, b[n0:n1].contiguous(), gt, n0, n1, counts=torch.zeros_like(counts))
+        s_sum += s
+    assert torch.equal(s_sum, s_full)
+    for ws, n0, n1 in splits:
+        ops.score_rank_tc(Q, ws, b[n0:n1].contiguous(), gt, n0, n1, s_gt=s_sum, counts=counts)
+    assert torch.equal(counts, full)
+    ref = (Q.double() @ W.double().t())
+    ref_rank = (ref > ref[torch.arange(n_q), gt].unsqueeze(1)).sum(1)
+    assert float((counts.cpu() - ref_rank.cpu()).abs().float().mean()) < 0.5     # near-tie flips only
