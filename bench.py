@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--score-path", type=str, default="tc", choices=["tc", "ffma"])
     ap.add_argument("--tc-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--all-rows", action="store_true",
+                    help="run the loss GEMMs on every row, including those whose target is ignore_index")
     return ap.parse_args()
 
 
@@ -212,11 +214,13 @@ def run_b200(a):
     adj, fields, ev = make_workload(hp, n_tb * world, a.eval_batches, seed=0)
     fields = fields[rank::world] if world > 1 else fields          # each rank its own sequences
     host_tb, host_eb = train_batches(fields, B, True), eval_batches(ev, Bq, True)
-    dev_tb = [tuple(x.to(dev) for x in b) for b in host_tb]
+    dev_tb = None        # device-resident batches come from the product's own loader (see below)
     dev_eb = [tuple(x.to(dev) for x in b) for b in host_eb]
     torch.manual_seed(hp.seed)
     ds = CDSRDataset.from_fields([fields[:, i] for i in range(14)], "train", L)
-    tr = Trainer.from_parts(hp, Quiet(), (BatchLoader(ds, B), None, None), adj[0], adj[1])
+    hp.skip_ignored_rows = not a.all_rows
+    loader = BatchLoader(ds, B, len_rec=R, ignore=(hp.n_item_a, hp.n_item_b))
+    tr = Trainer.from_parts(hp, Quiet(), (loader, None, None), adj[0], adj[1])
     model = tr.model
 
     def train_step(batches):
@@ -225,7 +229,9 @@ def run_b200(a):
             return tr.train_batch(batches[i % len(batches)])
         return f
 
-    # ---- training, inputs resident in HBM ----
+    # ---- training, inputs resident in HBM: batches sliced on the device by the package's BatchLoader ----
+    ds.to(dev)
+    dev_tb = list(loader)
     model.train()
     tr.optimizer.zero_grad()
     step = train_step(dev_tb)
@@ -286,7 +292,14 @@ def run_b200(a):
 
     pk = peaks()
     na, nb = hp.n_item_a, hp.n_item_b
-    flops_step = 3 * 2.0 * (2 * B * R) * d * (na + nb)              # fwd + 2x bwd, algorithmic
+    flops_ref = 3 * 2.0 * (2 * B * R) * d * (na + nb)               # fwd + 2x bwd over every row
+    # rows that carry a target (the others are ignore_index: exactly zero loss and gradient, not computed)
+    rows_frac = 1.0
+    if not a.all_rows:
+        used = [b.n_valid[0] for b in dev_tb if getattr(b, "n_valid", None)]
+        if used:
+            rows_frac = sum(ma * na + mb * nb for ma, mb in used) / (len(used) * (2.0 * B * R) * (na + nb))
+    flops_step = flops_ref * rows_frac                               # work the path actually needs
     ach = flops_step / (dom_ms / 1e3) / 1e12
     ev_flops = 2.0 * Bq * d * (na * 0.5 + nb * 0.5)                 # per batch, domain mix ~50/50
     ev_ach = ev_flops / (ev_dom_ms / 1e3) / 1e12
@@ -298,7 +311,8 @@ def run_b200(a):
         "config": {"workload": f"C2DSR {hp.dataset} shape, d={d}, L={L}, batch {B}/GPU, train step = convolve_graph"
                                " + train_batch (fwd, bwd, AdamW-amsgrad); + full-itemset eval",
                    "n_item_a": na, "n_item_b": nb, "len_rec": R, "dropout": a.dropout, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2_note": "working set per step (params + AdamW state 1.3 GB, "
+                   "parallelism": f"dp{world}", "loss_rows": "all" if a.all_rows else
+                   "rows with a target only (ignore_index rows contribute exactly 0 to loss and gradients)", "l2_note": "working set per step (params + AdamW state 1.3 GB, "
                    "logits 1.3 GB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": round(train_e2e, 2), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -306,7 +320,16 @@ def run_b200(a):
         "gpu_launches": int(launches),
         "roofline": {"kernel": "K4a classifier logits + cross-entropy (score_ce fwd+bwd, %d calls/step)" % n_dom_calls,
                      "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
-                     "frac": round(ach / pk["tensor"], 5), "traffic": None, "peak_source": pk["src"] + " sustained",
+                     "frac": round(ach / pk["tensor"], 5),
+                     # DRAM bytes of the K4a launches of one step, ncu --set full (profiles/r01_ncu_full_kernels.md)
+                     "traffic": 5.8e9 if (a.score_path == "tc" and a.workload == "fk" and a.tc_passes == 3) else None,
+                     "peak_source": pk["src"] + " sustained",
+                     "algorithmic_gflop_per_step": round(flops_step / 1e9, 1),
+                     "rows_with_target_frac": round(rows_frac, 4),
+                     "reference_algorithm_gflop_per_step": round(flops_ref / 1e9, 1),
+                     # tensor-core work actually issued: 4 GEMMs (forward, recompute, dH, dW) x passes MMAs per product
+                     "executed_tflops": round(ach * (4.0 / 3.0) * a.tc_passes, 1) if a.score_path == "tc" else round(ach, 1),
+                     "executed_frac": round(ach * (4.0 / 3.0) * a.tc_passes / pk["tensor"], 4) if a.score_path == "tc" else None,
                      "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / (ms / a.steps), 4),
                      "path": ("tcgen05 bf16x%d: fused log-sum-exp forward, recompute + 2 gradient GEMMs backward" % a.tc_passes)
                      if a.score_path == "tc" else "ffma fp32 (materialised logits)"},
@@ -317,6 +340,7 @@ def run_b200(a):
                          "d2h_bytes_per_step": Bq * 4},
                  "roofline": {"kernel": "K4b score + rank count", "bound": "tensor", "achieved": round(ev_ach, 3),
                               "peak": pk["tensor_burst"], "unit": "TFLOP/s", "frac": round(ev_ach / pk["tensor_burst"], 5),
+                              "executed_tflops": round(ev_ach * a.tc_passes, 1) if a.score_path == "tc" else round(ev_ach, 1),
                               "ms_per_batch": round(ev_dom_ms, 4), "peak_source": pk["src"] + " burst",
                               "path": ("tcgen05 bf16x%d, fused count" % a.tc_passes) if a.score_path == "tc" else "ffma fp32"}},
     }

@@ -118,6 +118,32 @@ __global__ void rank_count_kernel(const float* __restrict__ S, int64_t lds, cons
     }
 }
 
+// Stable partition of the row indices: rows whose target is not the ignore class first (original order),
+// ignored rows after them.  One block; each thread owns a contiguous slice, block-wide exclusive scan of counts.
+__global__ void compact_rows_kernel(const int64_t* __restrict__ gt, int64_t M, int64_t ignore, int64_t* __restrict__ perm) {
+    __shared__ int counts[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (M + blockDim.x - 1) / blockDim.x;
+    const int64_t lo = tid * per, hi = lo + per < M ? lo + per : M;
+    int c = 0;
+    for (int64_t i = lo; i < hi; ++i) c += gt[i] != ignore;
+    counts[tid] = c;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {               // inclusive Hillis-Steele scan
+        const int v = tid >= o ? counts[tid - o] : 0;
+        __syncthreads();
+        counts[tid] += v;
+        __syncthreads();
+    }
+    const int total = counts[blockDim.x - 1];
+    int64_t v_pos = counts[tid] - c;                         // valid rows before this slice
+    int64_t i_pos = total + (lo < M ? lo : M) - v_pos;       // ignored rows go after all valid ones
+    for (int64_t i = lo; i < hi; ++i) {
+        if (gt[i] != ignore) perm[v_pos++] = i;
+        else perm[i_pos++] = i;
+    }
+}
+
 }  // namespace c2dsr
 
 using namespace c2dsr;
@@ -131,6 +157,13 @@ using namespace c2dsr;
 extern "C" {
 
 int64_t c2dsr_score_ldz(int64_t N) { return align_up(N, 4); }
+
+int c2dsr_compact_rows(const int64_t* gt, int64_t M, int64_t ignore, int64_t* perm, void* stream) {
+    if (M <= 0) return C2DSR_OK;
+    compact_rows_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(gt, M, ignore, perm);
+    note_launches(1);
+    return check_launch("compact_rows");
+}
 
 int c2dsr_score_ce_fwd(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
                        int64_t M, int64_t N, int d, float* Z, float* lse, float* loss_row, void* workspace,

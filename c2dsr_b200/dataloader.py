@@ -181,6 +181,19 @@ class CDSRDataset(torch.utils.data.Dataset):
         self.length = len(self.fields[0])
         return self
 
+    def valid_counts(self, len_rec: int, na: int, nb: int):
+        """Host-side int64 [n, 2]: per training sample, the number of non-ignored targets in the last len_rec
+        positions for the A-domain losses (gt_share_a, gt_a) and the B-domain losses (gt_share_b, gt_b).
+        Lets the trainer size the loss GEMMs without asking the device (no host sync)."""
+        key = ("valid", len_rec, na, nb)
+        cache = self.__dict__.setdefault("_cache", {})
+        if key not in cache:
+            f = [self.fields[i][:, -len_rec:].cpu() for i in (6, 7, 8, 9)]
+            a = (f[0] != na).sum(1) + (f[2] != na).sum(1)
+            b = (f[1] != nb).sum(1) + (f[3] != nb).sum(1)
+            cache[key] = (torch.stack((a, b), 1), na, nb)
+        return cache[key]
+
     def to(self, device, pin: bool = False):
         """Make the whole split device-resident (or pinned) once -- 'next' row f-1."""
         if pin and torch.device(device).type == "cpu":
@@ -196,6 +209,11 @@ class CDSRDataset(torch.utils.data.Dataset):
         return tuple(x[index] for x in self.fields)
 
 
+class Batch(tuple):
+    """A batch tuple that can carry host-side facts about itself (``n_valid``: rows of the A / B loss GEMMs)."""
+    n_valid = None
+
+
 class BatchLoader:
     """Iterates whole batches as tuples of ``[B, ...]`` tensors sliced from ``dataset.fields``.
 
@@ -206,9 +224,12 @@ class BatchLoader:
     """
 
     def __init__(self, dataset: CDSRDataset, batch_size: int, shuffle: bool = False, rank: int = 0,
-                 world_size: int = 1):
+                 world_size: int = 1, len_rec: int = 0, ignore=None):
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
         self.rank, self.world_size = rank, world_size
+        # len_rec > 0 and ignore = (n_item_a, n_item_b): training batches carry the number of non-ignored loss rows
+        self.len_rec = len_rec if ignore is not None else 0
+        self.ignore = ignore
 
     def __len__(self):
         return (len(self.dataset) + self.batch_size - 1) // self.batch_size
@@ -224,16 +245,24 @@ class BatchLoader:
         else:
             order = None
         dev = self.dataset.fields[0].device
+        counts = None
+        if self.len_rec and self.dataset.mode == "train":
+            na, nb = self.ignore
+            counts, na, nb = self.dataset.valid_counts(self.len_rec, na, nb)
         for lo in range(0, n, self.batch_size):
             hi = min(lo + self.batch_size, n)
             if self.world_size > 1:                     # data-parallel: contiguous slice of the global batch
                 per = (hi - lo + self.world_size - 1) // self.world_size
                 lo, hi = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
             if order is None:
-                yield tuple(x[lo:hi] for x in self.dataset.fields)
+                out = Batch(x[lo:hi] for x in self.dataset.fields)
+                if counts is not None:
+                    out.n_valid = (tuple(int(v) for v in counts[lo:hi].sum(0)), na, nb)
             else:
-                idx = order[lo:hi].to(dev)
-                yield tuple(x.index_select(0, idx) for x in self.dataset.fields)
+                out = Batch(x.index_select(0, order[lo:hi].to(dev)) for x in self.dataset.fields)
+                if counts is not None:
+                    out.n_valid = (tuple(int(v) for v in counts.index_select(0, order[lo:hi]).sum(0)), na, nb)
+            yield out
 
 
 def count_item(path: str) -> int:
@@ -250,7 +279,8 @@ def get_dataloader(args):
     args.n_item = args.n_item_a + args.n_item_b + 1
     args.idx_pad = args.n_item - 1
     rank, world = getattr(args, "rank", 0), getattr(args, "world_size", 1)
-    train = BatchLoader(CDSRDataset(args, "train"), args.batch_size, shuffle=True, rank=rank, world_size=world)
+    train = BatchLoader(CDSRDataset(args, "train"), args.batch_size, shuffle=True, rank=rank, world_size=world,
+                        len_rec=getattr(args, "len_rec", 0), ignore=(args.n_item_a, args.n_item_b))
     val = BatchLoader(CDSRDataset(args, "val"), args.batch_size_eval)
     test = BatchLoader(CDSRDataset(args, "test"), args.batch_size_eval)
     return train, val, test

@@ -318,6 +318,14 @@ class ScoreCETcFn(torch.autograd.Function):
         return dH, dHpad, dW, db, dwpad, dbpad, None, None, None
 
 
+def compact_rows(gt: torch.Tensor, ignore: int) -> torch.Tensor:
+    """Stable partition of the row indices: rows with gt != ignore first (int64 [M])."""
+    gt = gt.contiguous()
+    perm = torch.empty_like(gt)
+    call("c2dsr_compact_rows", ptr(gt, I64), gt.numel(), ignore, ptr(perm, I64), stream())
+    return perm
+
+
 def score_ce(H, Hpad, W, b, wpad, bpad, gt, rowscale, path: str = "tc", passes: int = 3):
     """Weighted cross-entropy sum over the full catalogue; path 'tc' (tcgen05) or 'ffma' (fp32 CUDA cores)."""
     if path == "tc":

@@ -66,6 +66,8 @@ class Trainer(object):
         # "ffma": fp32 CUDA-core GEMMs with materialised scores (the comparison path)
         self.score_path = getattr(args, "score_path", "tc")
         self.tc_passes = int(getattr(args, "tc_passes", 3))
+        # skip loss rows whose target is ignore_index (exactly zero contribution); off = every row, like the reference
+        self.skip_ignored = bool(getattr(args, "skip_ignored_rows", True))
         self._wsplit = {}
         self.bucket = cdist.GradBucket()
 
@@ -122,6 +124,7 @@ class Trainer(object):
     # ------------------------------------------------------------------------------------------
     def losses(self, batch):
         """Forward part of trainer.py:91-154 -> (loss, loss_rec, loss_mi), differentiable."""
+        n_valid = self._valid_rows(batch)
         (seq_share, seq_a, seq_b, pos, pos_a, pos_b, gt_share_a, gt_share_b, gt_a, gt_b, gt_mask_a, gt_mask_b,
          seq_neg_a, seq_neg_b) = (x.to(self.device, non_blocking=True) for x in batch)
         m = self.model
@@ -142,17 +145,42 @@ class Trainer(object):
         ha, hb = hx[:, -R:].reshape(-1, d), hy[:, -R:].reshape(-1, d)
         share_w = (1.0 / (R * b_glob)).expand(B * R)
         parts = []
-        for h_dom, cls, g_share, g_dom, n_dom in ((ha, m.classifier_a, gt_share_a, g_a, n_a),
-                                                  (hb, m.classifier_b, gt_share_b, g_b, n_b)):
+        for k, (h_dom, cls, g_share, g_dom, n_dom) in enumerate(((ha, m.classifier_a, gt_share_a, g_a, n_a),
+                                                                 (hb, m.classifier_b, gt_share_b, g_b, n_b))):
             H = torch.cat((hs, hs + h_dom), 0)                 # item logits: h_share | h_share + h_dom
             Hpad = torch.cat((hs, h_dom), 0)                   # pad logit:   h_share | h_dom      (Q5)
             gt = torch.cat((g_share[:, -R:].reshape(-1), g_dom), 0)
             w = torch.cat((share_w, (1.0 / n_dom).expand(B * R)), 0)   # loss_share re-weighting (Q11)
+            if n_valid is not None:
+                # rows whose target is the ignore class add nothing to the loss or to any gradient: run the
+                # catalogue-wide GEMMs on the other rows only (a stable partition brings them to the front)
+                mv = n_valid[k]
+                if mv == 0:
+                    parts.append(hs.sum() * 0.0)
+                    continue
+                keep = ops.compact_rows(gt, cls.weight.shape[0])[:mv]
+                H, Hpad, gt, w = H.index_select(0, keep), Hpad.index_select(0, keep), gt[keep], w[keep]
             parts.append(ops.score_ce(H, Hpad, cls.weight, cls.bias, m.classifier_pad.weight, m.classifier_pad.bias,
                                       gt, w, path=self.score_path, passes=self.tc_passes))
         loss_rec = parts[0] + parts[1]
         loss = self.lambda_loss * loss_rec + (1 - self.lambda_loss) * loss_mi
         return loss, loss_rec, loss_mi
+
+    def _valid_rows(self, batch):
+        """(rows of the A-domain loss GEMM, rows of the B-domain one) that are not ignore_index, known on the
+        host: from the loader's bookkeeping, or from the batch itself while it is still in host memory.  Returns
+        None (= compute every row, as the reference does) when the option is off or the facts are on the device."""
+        if not self.skip_ignored:
+            return None
+        nv = getattr(batch, "n_valid", None)
+        if nv is not None and nv[1] == self.n_item_a and nv[2] == self.n_item_b:
+            return nv[0]
+        if not batch[6].is_cuda:
+            R = self.len_rec
+            f = [batch[i][:, -R:] for i in (6, 7, 8, 9)]
+            return (int((f[0] != self.n_item_a).sum() + (f[2] != self.n_item_a).sum()),
+                    int((f[1] != self.n_item_b).sum() + (f[3] != self.n_item_b).sum()))
+        return None
 
     def train_batch(self, batch):
         """trainer.py:91-160 -> (loss, loss_rec, loss_mi) as 0-d tensors (global values under DP)."""

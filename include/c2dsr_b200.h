@@ -172,6 +172,11 @@ int c2dsr_score_ce_bwd(const float* H, const float* W, const float* zpad, const 
                        const float* coef, int64_t M, int64_t N, int d, float* Z, float* dH, float* dW,
                        float* dbias, float* dzpad, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Rows whose target is the ignore class contribute neither loss nor gradient (F.cross_entropy ignore_index,
+ * trainer.py:143-152).  perm[M] = stable partition of 0..M-1 with the non-ignored rows first, so that the caller
+ * can run the calls above on the leading rows only. */
+int c2dsr_compact_rows(const int64_t* gt, int64_t M, int64_t ignore, int64_t* perm, void* stream);
+
 /* Tensor-core form of the two calls above (tcgen05 + TMA, bf16 hi/lo split with `passes` = 3 for
  * fp32-grade logits, 1 for plain bf16).  The fp32 logits are never written to HBM: the forward keeps
  * per-tile (max, sum-exp) pairs, the backward recomputes the logits, stores dZ as bf16 hi/lo and runs
