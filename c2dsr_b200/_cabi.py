@@ -175,13 +175,14 @@ def stream() -> int:
 
 
 class _Workspace:
-    """One growable scratch buffer per device; kernels on a stream run in order, so reuse is safe."""
+    """One growable scratch buffer per (device, stream); kernels on a stream run in order, so reuse is safe."""
 
     def __init__(self):
         self.buf = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        key = torch.device(device).index or 0
+        # one buffer per (device, stream): branches running on side streams must not share scratch
+        key = (torch.device(device).index or 0, torch.cuda.current_stream().cuda_stream)
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

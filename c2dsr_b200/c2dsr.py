@@ -111,6 +111,8 @@ class C2DSR(nn.Module):
         self.graph_share = adj if isinstance(adj, CsrGraph) else CsrGraph(adj, dev)
         self.graph_specific = adj_specific if isinstance(adj_specific, CsrGraph) else CsrGraph(adj_specific, dev)
         self.hi_share = self.hi_a = self.hi_b = None
+        self.branch_streams = bool(getattr(args, "branch_streams", True))
+        self._side = None
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
 
@@ -144,6 +146,10 @@ class C2DSR(nn.Module):
     def forward(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b):
         """models/C2DSR.py:64-77 -> (h_share, hx, hy), each fp32 [B, L, d]."""
         s = self._next_seed()
+        if self.branch_streams and seq_share.is_cuda:
+            return self._branch_set(((self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, 1),
+                                     (self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, 2),
+                                     (self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, 3)), s)
         return (self._branch(self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, s, 1),
                 self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2),
                 self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3))
@@ -160,7 +166,29 @@ class C2DSR(nn.Module):
         B = seq_share.shape[0]
         seq3 = torch.cat((seq_share, seq_neg_a, seq_neg_b), 0)
         pos3 = torch.cat((pos_share, pos_share, pos_share), 0)
-        h3 = self._branch(self.attn_share, self.embed_i, self.hi_share, seq3, pos3, s, 1)
-        hx = self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2)
-        hy = self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3)
+        if not (self.branch_streams and seq_share.is_cuda):
+            h3 = self._branch(self.attn_share, self.embed_i, self.hi_share, seq3, pos3, s, 1)
+            hx = self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2)
+            hy = self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3)
+        else:
+            h3, hx, hy = self._branch_set(((self.attn_share, self.embed_i, self.hi_share, seq3, pos3, 1),
+                                           (self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, 2),
+                                           (self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, 3)), s)
         return h3[:B], hx, hy, h3[B:2 * B], h3[2 * B:]
+
+    def _branch_set(self, branches, seed: int):
+        """Independent branches forked onto side streams inside one autograd node (ops.BranchSetFn); the
+        first branch stays on the caller's stream."""
+        if self._side is None or len(self._side) < len(branches) - 1:
+            self._side = tuple(torch.cuda.Stream() for _ in range(len(branches) - 1))
+        grad = torch.is_grad_enabled()
+        specs, flat = [], []
+        for attn, table, hi, seq, pos, tag in branches:
+            w = attn.weights()
+            specs.append(dict(seq=seq, pos=pos, scale=float(self.d_latent ** 0.5), pad=self.n_item - 1,
+                              p=attn.p if self.training else 0.0, seed=seed, gather_tag=tag * 2 + 1,
+                              encoder_tag=tag * 2, n_head=attn.n_head, norm_first=attn.norm_first,
+                              dense_passes=attn.dense_passes if grad else attn.dense_passes_eval, n_w=len(w)))
+            flat += [hi, table.weight, attn.pos_emb.weight, *w]
+        return ops.BranchSetFn.apply(specs, (None, *self._side[:len(branches) - 1]), *flat)
+

@@ -75,6 +75,26 @@ class GCNFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 # K1: branch input (models/C2DSR.py:65-71, models/encoders.py:30-31)
 # ------------------------------------------------------------------------------------------------
+def _gather_forward(hi, E, P, seq, pos, scale, p, seed, tag):
+    d = E.shape[1]
+    x = torch.empty(*seq.shape, d, device=E.device, dtype=F32)
+    call("c2dsr_gather_fwd", ptr(hi), ptr(E), ptr(P), ptr(seq, I64), ptr(pos, I64), ptr(x), seq.numel(),
+         d, scale, p, seed, tag, stream())
+    return x
+
+
+def _gather_backward(dx, seq, pos, n_rows, d, p_shape, scale, pad_idx, p, seed, tag):
+    d_hi = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
+    d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
+    d_P = torch.zeros(p_shape, device=dx.device, dtype=F32)
+    n = seq.numel()
+    nb = query("c2dsr_gather_bwd_workspace_bytes", n, d, n_rows, p_shape[0])
+    ws = workspace.get(nb, dx.device)
+    call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, n_rows, p_shape[0],
+         pad_idx, scale, p, seed, tag, ptr(ws), ws.numel(), stream())
+    return d_hi, d_E, d_P
+
+
 class GatherFn(torch.autograd.Function):
     """x = drop(sqrt(d) * (hi[seq] + E[seq]) + P[pos]);  seq, pos int64 of any shape -> [..., d]."""
 
@@ -82,10 +102,7 @@ class GatherFn(torch.autograd.Function):
     def forward(ctx, hi, E, P, seq, pos, scale: float, pad_idx: int, p: float, seed: int, tag: int):
         hi, E, P = _f(hi), _f(E), _f(P)
         seq_c, pos_c = seq.contiguous(), pos.contiguous()
-        d = E.shape[1]
-        x = torch.empty(*seq.shape, d, device=E.device, dtype=F32)
-        call("c2dsr_gather_fwd", ptr(hi), ptr(E), ptr(P), ptr(seq_c, I64), ptr(pos_c, I64), ptr(x), seq_c.numel(),
-             d, scale, p, seed, tag, stream())
+        x = _gather_forward(hi, E, P, seq_c, pos_c, scale, p, seed, tag)
         ctx.save_for_backward(seq_c, pos_c)
         ctx.cfg = (hi.shape, P.shape, scale, pad_idx, p, seed, tag)
         return x
@@ -94,15 +111,7 @@ class GatherFn(torch.autograd.Function):
     def backward(ctx, dx):
         seq, pos = ctx.saved_tensors
         (n_rows, d), p_shape, scale, pad_idx, p, seed, tag = ctx.cfg
-        dx = _f(dx)
-        d_hi = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
-        d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
-        d_P = torch.zeros(p_shape, device=dx.device, dtype=F32)
-        n = seq.numel()
-        nb = query("c2dsr_gather_bwd_workspace_bytes", n, d, n_rows, p_shape[0])
-        ws = workspace.get(nb, dx.device)
-        call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, n_rows, p_shape[0],
-             pad_idx, scale, p, seed, tag, ptr(ws), ws.numel(), stream())
+        d_hi, d_E, d_P = _gather_backward(_f(dx), seq, pos, n_rows, d, p_shape, scale, pad_idx, p, seed, tag)
         return d_hi, d_E, d_P, None, None, None, None, None, None, None
 
 
@@ -121,6 +130,32 @@ def _layer_table(tensors: Sequence[torch.Tensor], n_layers: int):
     return arr
 
 
+def _encoder_forward(x, seq, w, n_head, pad_idx, norm_first, p, seed, tag, dense_passes):
+    n_seq, L, d = x.shape
+    n_layers = (len(w) - 2) // 12
+    T = n_seq * L
+    saved = torch.empty(query("c2dsr_encoder_saved_floats", T, d, n_head, n_layers), device=x.device, dtype=F32)
+    out = torch.empty_like(x)
+    ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head, dense_passes), x.device)
+    table = _layer_table(w, n_layers)
+    call("c2dsr_encoder_fwd", C.addressof(table), n_layers, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), n_seq,
+         L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws),
+         ws.numel(), stream())
+    return out, saved
+
+
+def _encoder_backward(d_out, saved, seq, w, cfg):
+    n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers, dense_passes = cfg
+    grads = [torch.zeros_like(t) for t in w]
+    dx = torch.empty(n_seq, L, d, device=d_out.device, dtype=F32)
+    ws = workspace.get(query("c2dsr_encoder_workspace_bytes", n_seq * L, d, n_head, dense_passes), d_out.device)
+    wt, gt = _layer_table(w, n_layers), _layer_table(grads, n_layers)
+    call("c2dsr_encoder_bwd", C.addressof(wt), C.addressof(gt), n_layers, ptr(w[-2]), ptr(grads[-2]),
+         ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS,
+         p, seed, tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
+    return dx, grads
+
+
 class EncoderFn(torch.autograd.Function):
     """x [n_seq, L, d], seq [n_seq, L] -> encoder output.  ``weights`` = 12 tensors per layer in the
     order of _LAYER_FIELDS, then the final LayerNorm weight and bias."""
@@ -130,34 +165,92 @@ class EncoderFn(torch.autograd.Function):
                 dense_passes: int, *weights):
         x = _f(x)
         seq = seq.contiguous()
-        n_seq, L, d = x.shape
-        n_layers = (len(weights) - 2) // 12
         w = [_f(t) for t in weights]
-        T = n_seq * L
-        saved = torch.empty(query("c2dsr_encoder_saved_floats", T, d, n_head, n_layers), device=x.device, dtype=F32)
-        out = torch.empty_like(x)
-        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head, dense_passes), x.device)
-        table = _layer_table(w, n_layers)
-        call("c2dsr_encoder_fwd", C.addressof(table), n_layers, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), n_seq,
-             L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws),
-             ws.numel(), stream())
+        out, saved = _encoder_forward(x, seq, w, n_head, pad_idx, norm_first, p, seed, tag, dense_passes)
         ctx.save_for_backward(saved, seq, *w)
-        ctx.cfg = (n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers, dense_passes)
+        ctx.cfg = (*x.shape, n_head, pad_idx, norm_first, p, seed, tag, (len(w) - 2) // 12, dense_passes)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         saved, seq, *w = ctx.saved_tensors
-        n_seq, L, d, n_head, pad_idx, norm_first, p, seed, tag, n_layers, dense_passes = ctx.cfg
-        d_out = _f(d_out)
-        grads = [torch.zeros_like(t) for t in w]
-        dx = torch.empty(n_seq, L, d, device=d_out.device, dtype=F32)
-        ws = workspace.get(query("c2dsr_encoder_workspace_bytes", n_seq * L, d, n_head, dense_passes), d_out.device)
-        wt, gt = _layer_table(w, n_layers), _layer_table(grads, n_layers)
-        call("c2dsr_encoder_bwd", C.addressof(wt), C.addressof(gt), n_layers, ptr(w[-2]), ptr(grads[-2]),
-             ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS,
-             p, seed, tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
+        dx, grads = _encoder_backward(_f(d_out), saved, seq, w, ctx.cfg)
         return (dx, None, None, None, None, None, None, None, None, *grads)
+
+
+class BranchSetFn(torch.autograd.Function):
+    """Several independent branches (K1 gather + K3 encoder each) as ONE autograd node that forks them
+    onto CUDA streams and joins before returning, in forward and in backward.  One branch alone is too
+    small for 148 SMs (60-180 GEMM tiles); the autograd engine only ever sees the caller's stream, so
+    no cross-stream bookkeeping is left to it.
+
+    ``specs``: per branch a dict(seq, pos, scale, pad, p, seed, gather_tag, encoder_tag, n_head,
+    norm_first, dense_passes, n_w); ``streams``: per branch a torch.cuda.Stream or None (= the caller's
+    stream); ``flat``: per branch hi, E, P and the n_w encoder weights."""
+
+    @staticmethod
+    def forward(ctx, specs, streams, *flat):
+        cur = torch.cuda.current_stream()
+        outs, keep, off = [None] * len(specs), [], 0
+        parts = []
+        for sp in specs:
+            n = 3 + sp["n_w"]
+            parts.append([_f(t) for t in flat[off:off + n]])
+            off += n
+        order = sorted(range(len(specs)), key=lambda i: streams[i] is None)      # side streams first
+        for i in order:
+            sp, (hi, E, P, *w) = specs[i], parts[i]
+            seq, pos = sp["seq"].contiguous(), sp["pos"].contiguous()
+            st = streams[i] or cur
+            if st is not cur:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                x = _gather_forward(hi, E, P, seq, pos, sp["scale"], sp["p"], sp["seed"], sp["gather_tag"])
+                out, saved = _encoder_forward(x, seq, w, sp["n_head"], sp["pad"], sp["norm_first"], sp["p"],
+                                              sp["seed"], sp["encoder_tag"], sp["dense_passes"])
+                del x
+            outs[i] = out
+            keep.append((i, saved, seq, pos, hi.shape, P.shape, tuple(out.shape), len(w)))
+        for st in streams:
+            if st is not None:
+                cur.wait_stream(st)
+        ctx.specs, ctx.streams = specs, streams
+        ctx.meta = [(i, seq, pos, hs, ps, os, nw) for i, _, seq, pos, hs, ps, os, nw in keep]
+        ctx.save_for_backward(*[k[1] for k in keep], *[t for prt in parts for t in prt[3:]])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        specs, streams = ctx.specs, ctx.streams
+        nb = len(specs)
+        saved_all = ctx.saved_tensors
+        wts, off = [], nb
+        for sp in specs:
+            wts.append(list(saved_all[off:off + sp["n_w"]]))
+            off += sp["n_w"]
+        cur = torch.cuda.current_stream()
+        result = [None] * nb
+        for slot, (i, seq, pos, hi_shape, p_shape, o_shape, nw) in enumerate(ctx.meta):
+            sp, st = specs[i], streams[i] or cur
+            d_out = d_outs[i]
+            if d_out is None:
+                d_out = torch.zeros(o_shape, device=seq.device, dtype=F32)
+            d_out = _f(d_out)
+            if st is not cur:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                n_seq, L, d = o_shape
+                cfg = (n_seq, L, d, sp["n_head"], sp["pad"], sp["norm_first"], sp["p"], sp["seed"],
+                       sp["encoder_tag"], (nw - 2) // 12, sp["dense_passes"])
+                dx, grads = _encoder_backward(d_out, saved_all[slot], seq, wts[i], cfg)
+                d_hi, d_E, d_P = _gather_backward(dx, seq, pos, hi_shape[0], d, p_shape, sp["scale"], sp["pad"],
+                                                  sp["p"], sp["seed"], sp["gather_tag"])
+                del dx
+            result[i] = [d_hi, d_E, d_P, *grads]
+        for st in streams:
+            if st is not None:
+                cur.wait_stream(st)
+        return (None, None, *[t for r in result for t in r])
 
 
 # ------------------------------------------------------------------------------------------------
