@@ -191,8 +191,10 @@ def timed(fn, n, world):
     barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     for i in range(n):
         fn(i)
+    timed.host_ms = (time.perf_counter() - t0) * 1e3 / max(n, 1)      # host time to enqueue one step
     e1.record()
     barrier(world)
     return max_over_ranks(e0.elapsed_time(e1), world)
@@ -243,6 +245,14 @@ def run_b200(a):
     clk = ClockSampler(local_rank)
     ms = timed(step, a.steps, world)
     clocks = clk.stop()
+    # host time to enqueue a step, measured on 3 steps from an idle GPU (short enough not to fill the
+    # driver's launch queue, so the host is never blocked by the device)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(3):
+        step(i)
+    host_ms = (time.perf_counter() - t0) * 1e3 / 3
+    torch.cuda.synchronize()
     launches = _cabi.launch_count() - l0
     prof, _cabi.PROFILE = _cabi.PROFILE, None
     dom_ms = sum(e0.elapsed_time(e1) for _, e0, e1 in prof["events"]) / a.steps
@@ -311,7 +321,8 @@ def run_b200(a):
         "config": {"workload": f"C2DSR {hp.dataset} shape, d={d}, L={L}, batch {B}/GPU, train step = convolve_graph"
                                " + train_batch (fwd, bwd, AdamW-amsgrad); + full-itemset eval",
                    "n_item_a": na, "n_item_b": nb, "len_rec": R, "dropout": a.dropout, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "loss_rows": "all" if a.all_rows else
+                   "parallelism": f"dp{world}",
+                   "host_enqueue_ms_per_step": round(host_ms, 3), "loss_rows": "all" if a.all_rows else
                    "rows with a target only (ignore_index rows contribute exactly 0 to loss and gradients)", "l2_note": "working set per step (params + AdamW state 1.3 GB, "
                    "logits 1.3 GB) exceeds the 126 MB L2; no explicit flush"},
         "clocks": clocks,
@@ -322,7 +333,7 @@ def run_b200(a):
                      "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["tensor"], 5),
                      # DRAM bytes of the K4a launches of one step, ncu --set full (profiles/r01_ncu_full_kernels.md)
-                     "traffic": 5.8e9 if (a.score_path == "tc" and a.workload == "fk" and a.tc_passes == 3) else None,
+                     "traffic": 5.8e9 if (a.score_path == "tc" and a.workload == "fk" and a.tc_passes == 3 and a.all_rows) else None,
                      "peak_source": pk["src"] + " sustained",
                      "algorithmic_gflop_per_step": round(flops_step / 1e9, 1),
                      "rows_with_target_frac": round(rows_frac, 4),

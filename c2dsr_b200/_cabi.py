@@ -171,7 +171,8 @@ def ptr(t, dtype=None):
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw cudaStream_t of torch's current stream (the C-level getter: this runs ~150 times per step)."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 class _Workspace:
@@ -182,7 +183,7 @@ class _Workspace:
 
     def get(self, nbytes: int, device) -> torch.Tensor:
         # one buffer per (device, stream): branches running on side streams must not share scratch
-        key = (torch.device(device).index or 0, torch.cuda.current_stream().cuda_stream)
+        key = ((device if isinstance(device, torch.device) else torch.device(device)).index or 0, stream())
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
             b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

@@ -134,7 +134,7 @@ class Trainer(object):
         # normalisers are global-batch quantities under data parallelism
         g_a, g_b = gt_a[:, -R:].reshape(-1), gt_b[:, -R:].reshape(-1)
         counts = torch.stack(((g_a != self.n_item_a).sum(), (g_b != self.n_item_b).sum(),
-                              torch.tensor(B, device=self.device))).float()
+                              torch.full((), B, device=self.device))).float()     # (a fill: no host copy, no sync)
         cdist.allreduce_sum_(counts)
         n_a, n_b, b_glob = counts[0], counts[1], counts[2]
 
