@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--breakdown", action="store_true", help="also print a per-entry-point time table to stderr")
     ap.add_argument("--score-path", type=str, default="tc", choices=["tc", "ffma"])
     ap.add_argument("--tc-passes", type=int, default=3, choices=[1, 3])
+    ap.add_argument("--encoder-tc-passes", type=int, default=3, choices=[0, 1, 3],
+                    help="encoder dense layers in training: 0 = fp32 FFMA, 3 = tcgen05 bf16 hi/lo split")
     ap.add_argument("--all-rows", action="store_true",
                     help="run the loss GEMMs on every row, including those whose target is ignore_index")
     return ap.parse_args()
@@ -211,6 +213,7 @@ def run_b200(a):
     wl = WORKLOADS[a.workload]
     hp = hyper(wl, a.dropout, dev)
     hp.score_path, hp.tc_passes = a.score_path, a.tc_passes
+    hp.encoder_tc_passes = a.encoder_tc_passes
     B, Bq, L, d, R = hp.batch_size, hp.batch_size_eval, hp.len_max, hp.d_latent, hp.len_rec
     n_tb = min(a.steps + a.warmup, 24)
     adj, fields, ev = make_workload(hp, n_tb * world, a.eval_batches, seed=0)
@@ -322,6 +325,10 @@ def run_b200(a):
                                " + train_batch (fwd, bwd, AdamW-amsgrad); + full-itemset eval",
                    "n_item_a": na, "n_item_b": nb, "len_rec": R, "dropout": a.dropout, "global_batch": B * world,
                    "parallelism": f"dp{world}",
+                   "gemm_arithmetic": {"classifier": f"{a.score_path} passes={a.tc_passes}",
+                                       "encoder": f"passes={a.encoder_tc_passes}",
+                                       "note": "passes=3: fp32 operands split into bf16 hi+lo, 3 tcgen05 MMAs per "
+                                               "product, fp32 accumulate (product error ~1e-6); passes=0: fp32 FFMA"},
                    "host_enqueue_ms_per_step": round(host_ms, 3), "loss_rows": "all" if a.all_rows else
                    "rows with a target only (ignore_index rows contribute exactly 0 to loss and gradients)", "l2_note": "working set per step (params + AdamW state 1.3 GB, "
                    "logits 1.3 GB) exceeds the 126 MB L2; no explicit flush"},

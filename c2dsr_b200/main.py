@@ -42,6 +42,13 @@ FLAGS = [
     # this implementation
     ("--full_catalog", dict(action="store_true", help="rank against every item of the domain, not list_neg")),
     ("--save_processed", dict(action="store_true", help="with --use_raw: write the *.pkl files")),
+    ("--score_path", dict(type=str, default="tc", choices=["tc", "ffma"],
+                          help="classifier / ranking GEMMs: tcgen05 tensor cores or fp32 FFMA")),
+    ("--tc_passes", dict(type=int, default=3, choices=[1, 3],
+                         help="tensor-core products: 3 = bf16 hi/lo split (fp32-grade), 1 = plain bf16")),
+    ("--encoder_tc_passes", dict(type=int, default=3, choices=[0, 1, 3],
+                                 help="encoder projections while training: 0 = fp32 FFMA, 1 / 3 = tcgen05")),
+    ("--skip_ignored_rows", dict(type=int, default=1, help="0: run the loss GEMMs on ignore_index rows too")),
 ]
 
 

@@ -1,0 +1,41 @@
+"""Kernel-level device time (kineto) of a training step at the FK bench shape."""
+import sys, os, cProfile, pstats, argparse
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import torch
+import bench
+sys.argv = ["bench.py"]
+a = bench.parse()
+from c2dsr_b200.dataloader import BatchLoader, CDSRDataset
+from c2dsr_b200.trainer import Trainer
+dev = torch.device("cuda", 0)
+wl = bench.WORKLOADS["fk"]
+hp = bench.hyper(wl, 0.2, dev)
+hp.score_path, hp.tc_passes = "tc", 3
+adj, fields, ev = bench.make_workload(hp, 8, 1, seed=0)
+ds = CDSRDataset.from_fields([fields[:, i] for i in range(14)], "train", hp.len_max)
+loader = BatchLoader(ds, hp.batch_size, len_rec=hp.len_rec, ignore=(hp.n_item_a, hp.n_item_b))
+tr = Trainer.from_parts(hp, bench.Quiet(), (loader, None, None), adj[0], adj[1])
+ds.to(dev)
+tb = list(loader)
+tr.model.train(); tr.optimizer.zero_grad()
+def step(i):
+    tr.model.convolve_graph()
+    tr.train_batch(tb[i % len(tb)])
+for i in range(3): step(i)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+N = 5
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(N): step(i)
+    torch.cuda.synchronize()
+ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+agg = {}
+for e in ev:
+    k = e.name[:90]
+    a_ = agg.setdefault(k, [0, 0.0]); a_[0] += 1; a_[1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+tot = sum(v[1] for v in agg.values())
+print("total device-busy us/step (sum over streams):", tot / N)
+t0 = min(e.time_range.start for e in ev); t1 = max(e.time_range.end for e in ev)
+print("span us/step:", (t1 - t0) / N)
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k}")

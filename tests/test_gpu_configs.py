@@ -58,8 +58,9 @@ def _setup(d, L, n_head, n_attn, B, na=300, nb=700, seed=0, **over):
 
 @pytest.mark.parametrize("d,L,n_head,n_attn,B", [(512, 15, 1, 1, 32), (128, 50, 2, 1, 24), (256, 200, 1, 1, 6),
                                                  (512, 200, 4, 2, 4)])
-def test_sweep_corner_matches_oracle(d, L, n_head, n_attn, B):
-    tr, otr, batch, ebatch = _setup(d, L, n_head, n_attn, B)
+@pytest.mark.parametrize("dense", [0, 3])
+def test_sweep_corner_matches_oracle(d, L, n_head, n_attn, B, dense):
+    tr, otr, batch, ebatch = _setup(d, L, n_head, n_attn, B, encoder_tc_passes=dense)
     tr.model.train(); tr.optimizer.zero_grad(); otr.zero_grad()
     for step in range(2):
         tr.model.convolve_graph()

@@ -45,10 +45,13 @@ def _trainer_from_golden(g, state="init", **over):
     return tr
 
 
+@pytest.mark.parametrize("dense", [0, 3])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_training_steps_match_reference(name):
+def test_training_steps_match_reference(name, dense):
+    """dense = 0: encoder projections in fp32 FFMA; 3: on tcgen05 with the bf16 hi/lo split (the default)."""
     g = Golden(name)
-    tr = _trainer_from_golden(g)
+    tr = _trainer_from_golden(g, encoder_tc_passes=dense)
+    assert tr.model.attn_share.dense_passes == dense
     tr.model.train()                                   # dropouts are 0 in the fixtures
     tr.optimizer.zero_grad()
     ref_losses = g.z["losses"]
@@ -77,15 +80,20 @@ def test_training_steps_match_reference(name):
             assert all(p.grad is None for k, p in named.items() if ".encoder_layer." in k)   # Q3
     final = g.group("final")
     d, lr, n = g.hp["d_latent"], g.hp["lr"], len(ref_losses)
+    # AdamW's update is g / sqrt(v), so a parameter follows the *relative* error of its gradient element.  A
+    # ReLU unit flipped by the ~1e-6 product error of the tensor-core split changes the few-term sums behind
+    # a bias gradient of these tiny fixtures (d = 32, 320 tokens) by percents; losses stay within 1e-4 (above)
+    # and the fp32 FFMA mode keeps the 1e-3 bar on every parameter
+    w_tol = 1e-3 if dense == 0 else 3e-2
     for k, p in tr.model.state_dict().items():
         if k.endswith("attn_mask"):
             continue
         ref, got = final[k], p.cpu()
         if "in_proj" in k:
-            assert rel_err(got[2 * d:], ref[2 * d:]) < 1e-3, k
+            assert rel_err(got[2 * d:], ref[2 * d:]) < w_tol, k
             assert float((got[:2 * d] - ref[:2 * d]).abs().max()) <= 2 * n * lr, k
             continue
-        assert rel_err(got, ref) < 1e-3, k
+        assert rel_err(got, ref) < w_tol, k
 
 
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
