@@ -35,7 +35,7 @@ struct Dropout {
     float p;             // drop probability; 0 disables
     float inv_keep;      // 1 / (1 - p)
     uint32_t thresh;     // keep iff the element's 16-bit hash lane >= thresh
-    uint64_t key;        // seed mixed with the call-site tag
+    uint32_t k0, k1;     // per-(seed, call-site tag) keys of the two 32-bit hash words of a quad
 };
 
 static inline uint64_t host_mix64(uint64_t z) {
@@ -51,37 +51,48 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint64_t tag) {
     double t = (double)d.p * 65536.0 + 0.5;
     d.thresh = (uint32_t)(t > 65535.0 ? 65535.0 : t);                 // 16-bit threshold
     d.inv_keep = (float)(1.0 / (1.0 - (double)d.thresh / 65536.0));
-    d.key = host_mix64(seed ^ host_mix64(tag));
+    const uint64_t key = host_mix64(seed ^ host_mix64(tag));
+    d.k0 = (uint32_t)key;
+    d.k1 = (uint32_t)(key >> 32);
+    if (d.k1 == d.k0) d.k1 ^= 0x9E3779B9u;
     return d;
 }
 
-// One 64-bit mix serves FOUR consecutive elements: element idx keeps iff the 16-bit lane (idx & 3) of
-// mix(idx >> 2) is >= thresh (= round(p * 65536)); 1/(1-p) is taken from the quantised p so the mask stays
-// unbiased.  All kernels use these two helpers, so the mask of element idx is the same whether it is
-// generated one element or four at a time.
-__device__ __forceinline__ uint64_t mix64(uint64_t key, uint64_t quad) {
-    uint64_t z = key + quad * 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+// Counter-based mask.  Elements are hashed four at a time ("quad" = idx >> 2): two 32-bit words
+//   w_h = fmix32(quad ^ k_h),  h = 0, 1          (fmix32 = the murmur3 finaliser: full avalanche, 7 ALU ops)
+// give four 16-bit lanes; element idx keeps iff lane (idx & 3) >= thresh (= round(p * 65536)), and 1/(1-p) is
+// taken from the quantised p so the mask stays unbiased.  All kernels use these helpers, so the mask of
+// element idx is the same whether it is generated one element or four at a time, in forward or backward.
+// (A 64-bit splitmix per quad was 2-3x the instructions and made the SpMM gather issue-bound.)
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+__device__ __forceinline__ uint32_t quad_counter(uint64_t quad) {
+    return (uint32_t)quad ^ ((uint32_t)(quad >> 32) * 0x9E3779B1u);
 }
 
 // multiplicative mask value: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_scale(const Dropout& d, uint64_t idx) {
     if (d.p == 0.f) return 1.f;
-    const uint64_t z = mix64(d.key, idx >> 2);
-    const uint32_t h = (uint32_t)(z >> (16 * (idx & 3))) & 0xffffu;
+    const uint32_t w = fmix32(quad_counter(idx >> 2) ^ ((idx & 2) ? d.k1 : d.k0));
+    const uint32_t h = (idx & 1) ? (w >> 16) : (w & 0xffffu);
     return h >= d.thresh ? d.inv_keep : 0.f;
 }
 
 // four consecutive elements starting at a multiple of 4
 __device__ __forceinline__ void drop_scale4(const Dropout& d, uint64_t base, float4& v) {
     if (d.p == 0.f) return;
-    const uint64_t z = mix64(d.key, base >> 2);
-    v.x *= ((uint32_t)z & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
-    v.y *= ((uint32_t)(z >> 16) & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
-    v.z *= ((uint32_t)(z >> 32) & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
-    v.w *= (uint32_t)(z >> 48) >= d.thresh ? d.inv_keep : 0.f;
+    const uint32_t q = quad_counter(base >> 2);
+    const uint32_t w0 = fmix32(q ^ d.k0), w1 = fmix32(q ^ d.k1);
+    v.x *= (w0 & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
+    v.y *= (w0 >> 16) >= d.thresh ? d.inv_keep : 0.f;
+    v.z *= (w1 & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
+    v.w *= (w1 >> 16) >= d.thresh ? d.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,13 +1,14 @@
 // K2: CSR SpMM for the parameter-free GCN  out = alpha * A (.) X + beta * Y + gamma * Z.
 //
-// One warp per output row.  The row's (col, val) pairs are read once, 32 at a time, by the lanes
-// (coalesced) and handed round with shuffles; every lane then streams its float4 slice of each
+// A warp owns a few consecutive output rows.  Their (col, val) pairs are read once, 32 at a time, by
+// the lanes (coalesced) and handed round with shuffles; every lane then streams its float4 slice of each
 // gathered X row, so a row of d floats is one or two 512-byte coalesced requests per warp.  Rows
 // average ~4.5 non-zeros, but item popularity is heavy-tailed: rows longer than kLongRow non-zeros
-// are skipped by the warp-per-row kernel and handled by a second kernel, one 32-warp CTA per long
+// are skipped by the row-group kernel and handled by a second kernel, one 32-warp CTA per long
 // row: each warp sums a contiguous slice of the row's non-zeros and the 32 partials are added in warp
 // order, so the result has a fixed summation order.  HBM-bound: algorithmic bytes per row are
 // nnz_row * (8 + 4d) + 4 (rowptr) + 4d per addend + 4d written.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/c2dsr_b200.h"
 
@@ -73,26 +74,257 @@ __device__ __forceinline__ void finish_row(const SpmmArgs& a, int64_t row, int v
     reinterpret_cast<float4*>(a.out + row * a.d)[vi] = r;
 }
 
-template <int VPL>   // float4 vectors per lane: d <= 128 * VPL
+// RPW consecutive rows per warp.  The rows' non-zeros are one contiguous CSR range: the lanes read it
+// 32 entries at a time (coalesced), and the gathers of U entries are issued together, across row
+// boundaries, before any of them is consumed -- so a warp keeps U * VPL 512-byte requests in flight
+// and pays the rowptr -> (col, val) -> X dependency chain once per RPW rows instead of once per row
+// (rows average 4-5 non-zeros: the per-row chain, not bandwidth, bounded the one-row-per-warp form).
+// The accumulator is flushed whenever the flat entry index crosses a row end; every row is still
+// summed by one warp in CSR order, so results do not depend on the grouping.
+template <int VPL, int RPW, int U>   // float4 vectors per lane: d <= 128 * VPL
 __global__ void __launch_bounds__(256) spmm_kernel(SpmmArgs a, bool skip_long) {
     const int lane = threadIdx.x & 31;
     const int nv = a.d >> 2;
-    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    // persistent warps: rows are short (a few non-zeros), so each warp walks a strided set of rows instead of
-    // paying a block launch per 8 rows
-    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < a.n_rows; row += n_warps) {
-        const int beg = a.rowptr[row], end = a.rowptr[row + 1];
-        if (skip_long && end - beg > kLongRow) continue;
-        float4 acc[VPL];
+    const int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (r0 >= a.n_rows) return;
+    const int nr = a.n_rows - r0 < RPW ? (int)(a.n_rows - r0) : RPW;
+    const int rp = lane <= nr ? a.rowptr[r0 + lane] : 0;
+    const int lo = __shfl_sync(0xffffffffu, rp, 0), hi = __shfl_sync(0xffffffffu, rp, nr);
+    int cur = 0, row_beg = lo, row_end = __shfl_sync(0xffffffffu, rp, 1);
+    bool skip = skip_long && row_end - row_beg > kLongRow;
+    float4 acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&]() {
+        if (!skip) {
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int vi = lane + 32 * k;
+                if (vi < nv) finish_row(a, r0 + cur, vi, acc[k]);
+            }
+        }
 #pragma unroll
         for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        accumulate_range<VPL>(a, beg, end, lane, nv, acc);
+        ++cur;
+        row_beg = row_end;
+        row_end = __shfl_sync(0xffffffffu, rp, cur + 1 <= nr ? cur + 1 : nr);
+        skip = skip_long && row_end - row_beg > kLongRow;
+    };
+    for (int base = lo; base < hi; base += 32) {
+        const int mine = base + lane;
+        const int c_l = mine < hi ? a.col[mine] : 0;
+        const float v_l = mine < hi ? a.val[mine] : 0.f;
+        const int cnt = hi - base < 32 ? hi - base : 32;
+        for (int e0 = 0; e0 < cnt; e0 += U) {
+            float4 x[U][VPL];
+            int c[U];
 #pragma unroll
-        for (int k = 0; k < VPL; ++k) {
-            const int vi = lane + 32 * k;
-            if (vi < nv) finish_row(a, row, vi, acc[k]);
+            for (int u = 0; u < U; ++u) {
+                c[u] = __shfl_sync(0xffffffffu, c_l, (e0 + u) & 31);
+                if (e0 + u < cnt) {
+                    const float4* x4 = reinterpret_cast<const float4*>(a.X + (int64_t)c[u] * a.d);
+#pragma unroll
+                    for (int k = 0; k < VPL; ++k) {
+                        const int vi = lane + 32 * k;
+                        if (vi < nv) x[u][k] = __ldg(x4 + vi);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float v = __shfl_sync(0xffffffffu, v_l, (e0 + u) & 31);
+                if (e0 + u < cnt) {
+                    while (base + e0 + u >= row_end) flush();          // warp-uniform
+                    if (!skip) {
+#pragma unroll
+                        for (int k = 0; k < VPL; ++k) {
+                            const int vi = lane + 32 * k;
+                            if (vi < nv) {
+                                float4 xx = x[u][k];
+                                if (a.drop_mode == 1) drop_scale4(a.dr, (uint64_t)c[u] * a.d + 4 * vi, xx);
+                                acc[k].x += v * xx.x;
+                                acc[k].y += v * xx.y;
+                                acc[k].z += v * xx.z;
+                                acc[k].w += v * xx.w;
+                            }
+                        }
+                    }
+                }
+            }
         }
     }
+    while (cur < nr) flush();
+}
+
+// ---- bulk-copy (TMA) form ---------------------------------------------------------------------------
+// Same row grouping, but the gathered X rows are fetched by the copy engine: lane e issues ONE
+// cp.async.bulk (d * 4 bytes, global -> shared) for entry e of the current chunk, completion is counted on
+// an mbarrier, and the warp accumulates the chunk from shared memory while the next chunk is already in
+// flight (two stages per warp).  No registers are tied up by loads in flight and a 1 KB row costs one
+// instruction instead of 32 lanes x 2 LDG.128.  The addend rows Y / Z of the group are contiguous: one bulk
+// copy each, issued before the first gather, so that finishing a row never waits on a load (in the
+// one-row-per-warp form 58 % of the stall samples sat on the Y load of finish_row).
+constexpr int kBulkWarps = 4;              // warps per CTA
+constexpr int kBulkStages = 2;
+constexpr int kBulkStageBytes = 4096;      // per warp and stage: 4096 / (4 d) gathered rows
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_addr(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SPMM_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SPMM_DONE;\n\t"
+        "bra SPMM_WAIT;\n\t"
+        "SPMM_DONE:\n\t"
+        "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+template <int VPL, int RPW>
+__global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, bool skip_long, int chunk) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * (kBulkStages + 1);
+    const uint32_t row_bytes = (uint32_t)a.d * 4u;
+    const int n_add = (a.Y ? 1 : 0) + (a.Z ? 1 : 0);
+    const size_t per_warp = (size_t)kBulkStages * kBulkStageBytes + (size_t)n_add * RPW * row_bytes;
+    float* stage0 = reinterpret_cast<float*>(smem_raw + 128 + warp * per_warp);
+    float* ybuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage0) + kBulkStages * kBulkStageBytes);
+    float* zbuf = ybuf + (a.Y ? RPW * a.d : 0);
+    const int nv = a.d >> 2;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s <= kBulkStages; ++s) bar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int64_t r0 = ((int64_t)blockIdx.x * kBulkWarps + warp) * RPW;
+    if (r0 >= a.n_rows) return;
+    const int nr = a.n_rows - r0 < RPW ? (int)(a.n_rows - r0) : RPW;
+    const int rp = lane <= nr ? a.rowptr[r0 + lane] : 0;
+    if (n_add && lane == 0) {                                  // addend rows of the whole group: contiguous
+        bar_expect_tx(bars + kBulkStages, (uint32_t)(n_add * nr) * row_bytes);
+        if (a.Y) bulk_copy_g2s(ybuf, a.Y + r0 * a.d, (uint32_t)nr * row_bytes, bars + kBulkStages);
+        if (a.Z) bulk_copy_g2s(zbuf, a.Z + r0 * a.d, (uint32_t)nr * row_bytes, bars + kBulkStages);
+    }
+    bool add_ready = n_add == 0;
+    const int lo = __shfl_sync(0xffffffffu, rp, 0), hi = __shfl_sync(0xffffffffu, rp, nr);
+    int cur = 0, row_beg = lo, row_end = __shfl_sync(0xffffffffu, rp, 1);
+    bool skip = skip_long && row_end - row_beg > kLongRow;
+    float4 acc[VPL];
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto flush = [&]() {
+        if (!add_ready) {
+            bar_wait(bars + kBulkStages, 0);
+            add_ready = true;
+        }
+        if (!skip) {
+            const int64_t row = r0 + cur;
+#pragma unroll
+            for (int k = 0; k < VPL; ++k) {
+                const int vi = lane + 32 * k;
+                if (vi < nv) {
+                    float4 r = acc[k];
+                    if (a.drop_mode == 2) drop_scale4(a.dr, (uint64_t)row * a.d + 4 * vi, r);
+                    r.x *= a.alpha; r.y *= a.alpha; r.z *= a.alpha; r.w *= a.alpha;
+                    if (a.Y) {
+                        const float4 y = reinterpret_cast<const float4*>(ybuf + cur * a.d)[vi];
+                        r.x += a.beta * y.x; r.y += a.beta * y.y; r.z += a.beta * y.z; r.w += a.beta * y.w;
+                    }
+                    if (a.Z) {
+                        const float4 z = reinterpret_cast<const float4*>(zbuf + cur * a.d)[vi];
+                        r.x += a.gamma * z.x; r.y += a.gamma * z.y; r.z += a.gamma * z.z; r.w += a.gamma * z.w;
+                    }
+                    reinterpret_cast<float4*>(a.out + row * a.d)[vi] = r;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ++cur;
+        row_beg = row_end;
+        row_end = __shfl_sync(0xffffffffu, rp, cur + 1 <= nr ? cur + 1 : nr);
+        skip = skip_long && row_end - row_beg > kLongRow;
+    };
+    const int n_chunks = (hi - lo + chunk - 1) / chunk;
+    int c_s[kBulkStages];
+    float v_s[kBulkStages];
+    uint32_t phase = 0;                                  // bit s = parity to wait for on stage s
+    auto issue = [&](int k, int s) {
+        const int beg = lo + k * chunk;
+        const int cnt = hi - beg < chunk ? hi - beg : chunk;
+        int c = 0;
+        float v = 0.f;
+        if (lane < cnt) {
+            c = a.col[beg + lane];
+            v = a.val[beg + lane];
+        }
+        if (lane == 0) bar_expect_tx(bars + s, (uint32_t)cnt * row_bytes);
+        __syncwarp();
+        if (lane < cnt)
+            bulk_copy_g2s(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * kBulkStageBytes + (size_t)lane * row_bytes,
+                          a.X + (int64_t)c * a.d, row_bytes, bars + s);
+#pragma unroll
+        for (int t = 0; t < kBulkStages; ++t)
+            if (t == s) {
+                c_s[t] = c;
+                v_s[t] = v;
+            }
+    };
+#pragma unroll
+    for (int s = 0; s < kBulkStages; ++s)
+        if (s < n_chunks) issue(s, s);
+    for (int k = 0; k < n_chunks; ++k) {
+        const int s = k % kBulkStages;
+        bar_wait(bars + s, (phase >> s) & 1u);
+        phase ^= 1u << s;
+        const int beg = lo + k * chunk;
+        const int cnt = hi - beg < chunk ? hi - beg : chunk;
+        int c_l = 0;
+        float v_l = 0.f;
+#pragma unroll
+        for (int t = 0; t < kBulkStages; ++t)
+            if (t == s) {
+                c_l = c_s[t];
+                v_l = v_s[t];
+            }
+        const float4* st4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * kBulkStageBytes);
+        for (int e = 0; e < cnt; ++e) {
+            while (beg + e >= row_end) flush();                      // warp-uniform
+            const float v = __shfl_sync(0xffffffffu, v_l, e);
+            const int c = __shfl_sync(0xffffffffu, c_l, e);
+            if (!skip) {
+#pragma unroll
+                for (int q = 0; q < VPL; ++q) {
+                    const int vi = lane + 32 * q;
+                    if (vi < nv) {
+                        float4 xx = st4[e * nv + vi];
+                        if (a.drop_mode == 1) drop_scale4(a.dr, (uint64_t)c * a.d + 4 * vi, xx);
+                        acc[q].x += v * xx.x;
+                        acc[q].y += v * xx.y;
+                        acc[q].z += v * xx.z;
+                        acc[q].w += v * xx.w;
+                    }
+                }
+            }
+        }
+        __syncwarp();                                                // stage s fully read before it is refilled
+        if (k + kBulkStages < n_chunks) issue(k + kBulkStages, s);
+    }
+    while (cur < nr) flush();
 }
 
 // one CTA of 32 warps per long row; dynamic smem = 32 * d floats
@@ -140,13 +372,30 @@ extern "C" int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float
     C2DSR_REQUIRE(X != out, "spmm cannot run in place on X");
     SpmmArgs a{rowptr, col, val, X, Y, Z, out, n_rows, d, alpha, beta, gamma, drop_mode, make_dropout(p, seed, tag)};
     if (a.dr.p == 0.f) a.drop_mode = 0;
-    const unsigned blocks = (unsigned)ceil_div(n_rows, 8);     // one warp per row (a persistent, strided variant measured 10 % slower)
+    constexpr int kRowsPerWarp = 4;
+    const unsigned blocks = (unsigned)ceil_div(n_rows, 8 * kRowsPerWarp);
     cudaStream_t st = (cudaStream_t)stream;
     const bool split = long_rows != nullptr && n_long > 0;
     const int smem = 32 * d * 4;
+    const int n_add = (Y ? 1 : 0) + (Z ? 1 : 0);
+    const int bulk_smem = 128 + kBulkWarps * (kBulkStages * kBulkStageBytes + n_add * kRowsPerWarp * d * 4);
+    const int chunk = kBulkStageBytes / (4 * d) < 32 ? kBulkStageBytes / (4 * d) : 32;
+    static const char* force = getenv("C2DSR_SPMM");            // "warp" / "bulk": benchmarking override
+    const bool bulk = chunk >= 1 && (d % 4) == 0 && bulk_smem <= 200 * 1024 &&
+                      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(Z)) & 15) == 0 &&
+                      !(force && force[0] == 'w');
+    const unsigned bulk_blocks = (unsigned)ceil_div(n_rows, kBulkWarps * kRowsPerWarp);
 #define LAUNCH(V)                                                                                        \
     do {                                                                                                 \
-        spmm_kernel<V><<<blocks, 256, 0, st>>>(a, split);                                                \
+        if (bulk) {                                                                                      \
+            static bool battr = false;                                                                   \
+            if (!battr) {                                                                                \
+                cudaFuncSetAttribute(spmm_bulk_kernel<V, kRowsPerWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+                battr = true;                                                                            \
+            }                                                                                            \
+            spmm_bulk_kernel<V, kRowsPerWarp><<<bulk_blocks, 32 * kBulkWarps, bulk_smem, st>>>(a, split, chunk); \
+        } else                                                                                           \
+            spmm_kernel<V, kRowsPerWarp, (V <= 2 ? 8 / V : 2)><<<blocks, 256, 0, st>>>(a, split);        \
         if (split) {                                                                                     \
             static bool attr = false;                                                                    \
             if (!attr) {                                                                                 \
