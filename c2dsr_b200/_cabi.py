@@ -77,6 +77,11 @@ _PROTOS = {
     "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp]),
     "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp]),
     "c2dsr_adamw_amsgrad": (i32, [vp, i32, i64, f32, f32, f32, f32, f32, i32, vp]),
+    "c2dsr_step_state_bytes": (i32, []),
+    "c2dsr_step_state_set": (i32, [vp, i64, f32, vp]),
+    "c2dsr_step_state_set_lr": (i32, [vp, f32, vp]),
+    "c2dsr_step_begin": (i32, [vp, u64, vp]),
+    "c2dsr_adamw_amsgrad_dyn": (i32, [vp, i32, i64, vp, f32, f32, f32, f32, vp]),
     "c2dsr_axpby": (i32, [vp, vp, vp, i64, f32, f32, vp]),
 }
 EXPORTS = tuple(_PROTOS)
@@ -137,19 +142,38 @@ def call(name: str, *args):
     lib = _lib if (_lib is not None and _device_ok) else load()
     prof = PROFILE
     if prof is not None and (prof["names"] is None or name in prof["names"]):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a stream capture the events become event-record nodes that are re-timed on every replay
+        ext = torch.cuda.is_current_stream_capturing()
+        e0 = torch.cuda.Event(enable_timing=True, external=ext)
+        e1 = torch.cuda.Event(enable_timing=True, external=ext)
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        prof["events"].append((name, e0, e1))
+        (prof.setdefault("graph_events", []) if ext else prof["events"]).append((name, e0, e1))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:
         raise C2dsrError(f"{name} failed ({rc}): {lib.c2dsr_last_error().decode()}")
 
 
+# kernel launches replayed from CUDA graphs (the C-side counter only sees launches made through call())
+REPLAYED_LAUNCHES = 0
+
+
 def launch_count() -> int:
-    return int(load(check_device=False).c2dsr_launch_count())
+    return int(load(check_device=False).c2dsr_launch_count()) + REPLAYED_LAUNCHES
+
+
+class DynSeed(int):
+    """A dropout 'seed' that is the device address of c2dsr_step_state.key (see the header): ops pass it with
+    tag | SEED_INDIRECT so that kernels read the per-step key words themselves."""
+
+
+SEED_INDIRECT = 1 << 63
+
+
+def seed_tag(seed, tag: int) -> int:
+    return (tag | SEED_INDIRECT) if isinstance(seed, DynSeed) else tag
 
 
 def query(name: str, *args) -> int:
@@ -180,12 +204,16 @@ class _Workspace:
 
     def __init__(self):
         self.buf = {}
+        self.pinned = False      # set once a CUDA graph has captured a scratch address: regrown buffers are kept
+        self.retired = []
 
     def get(self, nbytes: int, device) -> torch.Tensor:
         # one buffer per (device, stream): branches running on side streams must not share scratch
         key = ((device if isinstance(device, torch.device) else torch.device(device)).index or 0, stream())
         b = self.buf.get(key)
         if b is None or b.numel() < nbytes:
+            if b is not None and self.pinned:
+                self.retired.append(b)
             b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
             self.buf[key] = b
         return b

@@ -114,6 +114,7 @@ class C2DSR(nn.Module):
         self.hi_share = self.hi_a = self.hi_b = None
         self.branch_streams = bool(getattr(args, "branch_streams", True))
         self._side = None
+        self.dyn_seed = None
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
 
@@ -128,6 +129,8 @@ class C2DSR(nn.Module):
 
     # ---- dropout stream: a fresh seed per forward pass, tags per site ----
     def _next_seed(self) -> int:
+        if self.dyn_seed is not None and self.training:
+            return self.dyn_seed           # device-resident per-step key (Trainer / CUDA-graph replay)
         self._calls += 1
         return (self._seed + 0x9E3779B97F4A7C15 * self._calls) & 0xFFFFFFFFFFFFFFFF
 

@@ -36,7 +36,10 @@ struct Dropout {
     float inv_keep;      // 1 / (1 - p)
     uint32_t thresh;     // keep iff the element's 16-bit hash lane >= thresh
     uint32_t k0, k1;     // per-(seed, call-site tag) keys of the two 32-bit hash words of a quad
+    const uint2* dyn;    // optional device-resident per-step key words XORed into k0 / k1 (see C2DSR_SEED_INDIRECT)
 };
+
+constexpr uint64_t kSeedIndirect = 1ull << 63;   // tag bit: ``seed`` is a device pointer to two uint32 key words
 
 static inline uint64_t host_mix64(uint64_t z) {
     z += 0x9E3779B97F4A7C15ull;
@@ -51,6 +54,12 @@ static inline Dropout make_dropout(float p, uint64_t seed, uint64_t tag) {
     double t = (double)d.p * 65536.0 + 0.5;
     d.thresh = (uint32_t)(t > 65535.0 ? 65535.0 : t);                 // 16-bit threshold
     d.inv_keep = (float)(1.0 / (1.0 - (double)d.thresh / 65536.0));
+    d.dyn = nullptr;
+    if (tag & kSeedIndirect) {            // the per-step part of the key lives on the device (CUDA-graph replay)
+        d.dyn = reinterpret_cast<const uint2*>(seed);
+        seed = 0;
+        tag &= ~kSeedIndirect;
+    }
     const uint64_t key = host_mix64(seed ^ host_mix64(tag));
     d.k0 = (uint32_t)key;
     d.k1 = (uint32_t)(key >> 32);
@@ -79,7 +88,12 @@ __device__ __forceinline__ uint32_t quad_counter(uint64_t quad) {
 // multiplicative mask value: 0 or 1/(1-p)
 __device__ __forceinline__ float drop_scale(const Dropout& d, uint64_t idx) {
     if (d.p == 0.f) return 1.f;
-    const uint32_t w = fmix32(quad_counter(idx >> 2) ^ ((idx & 2) ? d.k1 : d.k0));
+    uint32_t k = (idx & 2) ? d.k1 : d.k0;
+    if (d.dyn) {
+        const uint2 kk = __ldg(d.dyn);
+        k ^= (idx & 2) ? kk.y : kk.x;
+    }
+    const uint32_t w = fmix32(quad_counter(idx >> 2) ^ k);
     const uint32_t h = (idx & 1) ? (w >> 16) : (w & 0xffffu);
     return h >= d.thresh ? d.inv_keep : 0.f;
 }
@@ -88,7 +102,13 @@ __device__ __forceinline__ float drop_scale(const Dropout& d, uint64_t idx) {
 __device__ __forceinline__ void drop_scale4(const Dropout& d, uint64_t base, float4& v) {
     if (d.p == 0.f) return;
     const uint32_t q = quad_counter(base >> 2);
-    const uint32_t w0 = fmix32(q ^ d.k0), w1 = fmix32(q ^ d.k1);
+    uint32_t k0 = d.k0, k1 = d.k1;
+    if (d.dyn) {
+        const uint2 kk = __ldg(d.dyn);
+        k0 ^= kk.x;
+        k1 ^= kk.y;
+    }
+    const uint32_t w0 = fmix32(q ^ k0), w1 = fmix32(q ^ k1);
     v.x *= (w0 & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;
     v.y *= (w0 >> 16) >= d.thresh ? d.inv_keep : 0.f;
     v.z *= (w1 & 0xffffu) >= d.thresh ? d.inv_keep : 0.f;

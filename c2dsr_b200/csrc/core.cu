@@ -119,8 +119,35 @@ __global__ void wsum_kernel(const float* __restrict__ x, const float* __restrict
 
 // ------------------------------------------------------------------------------------------
 // AdamW + amsgrad over a table of tensors.  grid = (chunks, n_tensors).
+__global__ void step_set_kernel(c2dsr_step_state* s, int64_t step, float lr, bool set_step, bool set_lr) {
+    if (set_step) s->step = (uint64_t)step;
+    if (set_lr) s->lr = lr;
+}
+
+// advance to the next step: counter + the two per-step dropout key words derived from it
+__global__ void step_begin_kernel(c2dsr_step_state* s, uint64_t seed_base) {
+    const uint64_t t = s->step + 1;
+    s->step = t;
+    const uint32_t lo = (uint32_t)t, hi = (uint32_t)(t >> 32);
+    s->key[0] = fmix32((lo * 0x9E3779B1u) ^ (hi * 0x85EBCA77u) ^ (uint32_t)seed_base);
+    s->key[1] = fmix32(((lo + 0x632BE5ABu) * 0xC2B2AE3Du) ^ (hi * 0x27D4EB2Fu) ^ (uint32_t)(seed_base >> 32));
+}
+
 __global__ void adamw_kernel(const c2dsr_adam_tensor* __restrict__ table, float lr, float beta1, float beta2,
-                             float eps, float wd, float inv_bc1, float sqrt_bc2) {
+                             float eps, float wd, float inv_bc1, float sqrt_bc2,
+                             const c2dsr_step_state* __restrict__ state) {
+    if (state) {                       // step number and learning rate live on the device (CUDA-graph replay)
+        __shared__ float bc[2];
+        if (threadIdx.x == 0) {        // double-precision pow once per block, as the host path computes it
+            const double n = (double)state->step;
+            bc[0] = (float)(1.0 / (1.0 - pow((double)beta1, n)));
+            bc[1] = (float)sqrt(1.0 - pow((double)beta2, n));
+        }
+        __syncthreads();
+        lr = state->lr;
+        inv_bc1 = bc[0];
+        sqrt_bc2 = bc[1];
+    }
     const c2dsr_adam_tensor t = table[blockIdx.y];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float decay = 1.f - lr * wd;
@@ -226,6 +253,43 @@ int c2dsr_wsum(const float* x, const float* w, int64_t n, float* out, void* stre
     return check_launch("wsum");
 }
 
+int c2dsr_step_state_bytes(void) { return (int)sizeof(c2dsr_step_state); }
+
+int c2dsr_step_state_set(void* state, int64_t step, float lr, void* stream) {
+    C2DSR_REQUIRE(state != nullptr && step >= 0, "bad arguments");
+    step_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<c2dsr_step_state*>(state), step, lr, step >= 0,
+                                                       true);
+    note_launches(1);
+    return check_launch("step_state_set");
+}
+
+int c2dsr_step_state_set_lr(void* state, float lr, void* stream) {
+    C2DSR_REQUIRE(state != nullptr, "bad arguments");
+    step_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<c2dsr_step_state*>(state), 0, lr, false, true);
+    note_launches(1);
+    return check_launch("step_state_set_lr");
+}
+
+int c2dsr_step_begin(void* state, uint64_t seed_base, void* stream) {
+    C2DSR_REQUIRE(state != nullptr, "bad arguments");
+    step_begin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<c2dsr_step_state*>(state), seed_base);
+    note_launches(1);
+    return check_launch("step_begin");
+}
+
+int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, const void* state,
+                            float beta1, float beta2, float eps, float weight_decay, void* stream) {
+    if (n_tensors <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(state != nullptr, "state must not be NULL");
+    int64_t chunks = ceil_div(max_n, 256 * 4);
+    if (chunks > 148 * 8) chunks = 148 * 8;
+    if (chunks < 1) chunks = 1;
+    adamw_kernel<<<dim3((unsigned)chunks, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(
+        table_dev, 0.f, beta1, beta2, eps, weight_decay, 0.f, 0.f, reinterpret_cast<const c2dsr_step_state*>(state));
+    note_launches(1);
+    return check_launch("adamw_amsgrad_dyn");
+}
+
 int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, void* stream) {
     if (n_tensors <= 0) return C2DSR_OK;
@@ -235,7 +299,7 @@ int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64
     if (chunks > 148 * 8) chunks = 148 * 8;
     if (chunks < 1) chunks = 1;
     adamw_kernel<<<dim3((unsigned)chunks, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(
-        table_dev, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1), (float)sqrt(bc2));
+        table_dev, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1), (float)sqrt(bc2), nullptr);
     note_launches(1);
     return check_launch("adamw_amsgrad");
 }

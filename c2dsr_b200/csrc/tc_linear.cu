@@ -90,27 +90,65 @@ __global__ void linear_slab_reduce_kernel(const float* __restrict__ part, int sl
     }
 }
 
-// fp32 [rows, cols] with leading dimension ld_in -> bf16 hi / lo [rows, ld_out]
-__global__ void split_ld_kernel(const float* __restrict__ X, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out,
-                                uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-    const int64_t total = rows * cols;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols, c = i % cols;
+// fp32 [rows, cols] with leading dimension ld_in -> bf16 hi / lo [rows, ld_out].  Both operands of a product
+// are split by ONE launch (the first blocks_a blocks take job a, the rest job b); rows whose length and
+// strides are multiples of 4 go through 16-byte loads and 8-byte stores.
+struct SplitJob {
+    const float* X;
+    int64_t rows, cols, ld_in, ld_out;
+    uint16_t* hi;
+    uint16_t* lo;
+};
+
+__device__ __forceinline__ void split_job(const SplitJob& j, int64_t bid, int64_t nblk) {
+    const bool vec = ((j.cols | j.ld_in | j.ld_out) & 3) == 0 && (reinterpret_cast<uintptr_t>(j.X) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(j.hi) | reinterpret_cast<uintptr_t>(j.lo)) & 7) == 0;
+    if (vec) {
+        const int64_t c4n = j.cols >> 2, total = j.rows * c4n;
+        for (int64_t i = bid * blockDim.x + threadIdx.x; i < total; i += nblk * blockDim.x) {
+            const int64_t r = i / c4n, c = (i - r * c4n) << 2;
+            const float4 x = *reinterpret_cast<const float4*>(j.X + r * j.ld_in + c);
+            uint16_t h[4], l[4];
+            split2(x.x, h[0], l[0]);
+            split2(x.y, h[1], l[1]);
+            split2(x.z, h[2], l[2]);
+            split2(x.w, h[3], l[3]);
+            uint2 ph, pl;
+            ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+            ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+            pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
+            pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+            *reinterpret_cast<uint2*>(j.hi + r * j.ld_out + c) = ph;
+            if (j.lo) *reinterpret_cast<uint2*>(j.lo + r * j.ld_out + c) = pl;
+        }
+        return;
+    }
+    const int64_t total = j.rows * j.cols;
+    for (int64_t i = bid * blockDim.x + threadIdx.x; i < total; i += nblk * blockDim.x) {
+        const int64_t r = i / j.cols, c = i % j.cols;
         uint16_t h, l;
-        split2(X[r * ld_in + c], h, l);
-        hi[r * ld_out + c] = h;
-        if (lo) lo[r * ld_out + c] = l;
+        split2(j.X[r * j.ld_in + c], h, l);
+        j.hi[r * j.ld_out + c] = h;
+        if (j.lo) j.lo[r * j.ld_out + c] = l;
     }
 }
 
-static int split_ld(const float* X, int64_t rows, int64_t cols, int64_t ld_in, int64_t ld_out, uint16_t* hi,
-                    uint16_t* lo, cudaStream_t st) {
-    if (rows <= 0 || cols <= 0) return C2DSR_OK;
-    int64_t blocks = ceil_div(rows * cols, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    split_ld_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, cols, ld_in, ld_out, hi, lo);
+__global__ void split_pair_kernel(SplitJob a, SplitJob b, int blocks_a) {
+    if ((int)blockIdx.x < blocks_a) split_job(a, blockIdx.x, blocks_a);
+    else split_job(b, blockIdx.x - blocks_a, gridDim.x - blocks_a);
+}
+
+static int split_blocks(const SplitJob& j) {
+    int64_t blocks = ceil_div(j.rows * j.cols, 256 * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    return blocks < 1 ? 1 : (int)blocks;
+}
+
+static int split_pair(const SplitJob& a, const SplitJob& b, cudaStream_t st) {
+    const int na = split_blocks(a), nb = split_blocks(b);
+    split_pair_kernel<<<(unsigned)(na + nb), 256, 0, st>>>(a, b, na);
     note_launches(1);
-    return check_launch("split_ld");
+    return check_launch("split_pair");
 }
 
 constexpr int kLBN = 128, kLStages = 3;
@@ -153,11 +191,12 @@ int gemm_tc_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, const floa
     float* slabs = (float*)p;
     int rc;
     // ta = 0: A is [M, K] (K-major operand); ta = 1: A is stored [K, M] (MN-major operand)
-    if ((rc = ta ? split_ld(A, K, M, lda, ldm, a_hi, split ? a_lo : nullptr, st)
-                 : split_ld(A, M, K, lda, ldk, a_hi, split ? a_lo : nullptr, st))) return rc;
     // tb = 1: B is stored [N, K] (K-major operand); tb = 0: B is [K, N] (MN-major operand)
-    if ((rc = tb ? split_ld(B, N, K, ldb, ldk, b_hi, split ? b_lo : nullptr, st)
-                 : split_ld(B, K, N, ldb, ldn, b_hi, split ? b_lo : nullptr, st))) return rc;
+    const SplitJob ja = ta ? SplitJob{A, K, M, lda, ldm, a_hi, split ? a_lo : nullptr}
+                           : SplitJob{A, M, K, lda, ldk, a_hi, split ? a_lo : nullptr};
+    const SplitJob jb = tb ? SplitJob{B, N, K, ldb, ldk, b_hi, split ? b_lo : nullptr}
+                           : SplitJob{B, K, N, ldb, ldn, b_hi, split ? b_lo : nullptr};
+    if ((rc = split_pair(ja, jb, st))) return rc;
     const bool a_mn = ta != 0, b_mn = tb == 0;
     tc::Maps maps;
     if ((rc = make_maps<kLBN>(&maps, a_hi, a_lo, M, a_mn ? ldm : ldk, b_hi, b_lo, N, b_mn ? ldn : ldk, K, passes, a_mn,

@@ -59,9 +59,9 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
 class GradBucket:
     """Flat fp32 buffer holding a copy of every live gradient, all-reduced in one call.
 
-    The local ``p.grad`` keep accumulating across the batches of an epoch (reference semantics,
-    trainer.py:42 vs :157); all-reduce is linear, so reducing the accumulated local gradients
-    gives the accumulated global gradient.  The optimiser then reads the reduced views.
+    Each step's local gradients are summed over the ranks; the optimiser adds the reduced views to its
+    per-epoch gradient sums (reference semantics: gradients accumulate across the batches of an epoch,
+    trainer.py:42 vs :157; all-reduce is linear, so the order of the two sums does not matter).
     """
 
     def __init__(self):

@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _cabi
-from ._cabi import LayerWeights, call, ptr, query, stream, workspace
+from ._cabi import LayerWeights, call, ptr, query, seed_tag, stream, workspace
 
 F32, I64, I32 = torch.float32, torch.int64, torch.int32
 LN_EPS = 1e-8          # models/encoders.py:24-27 of the reference
@@ -31,7 +31,7 @@ def spmm(csr, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_
     out = torch.empty_like(X) if out is None else out
     call("c2dsr_spmm", ptr(rowptr, I32), ptr(col, I32), ptr(val, F32), ptr(long_rows),
          0 if long_rows is None else long_rows.numel(), ptr(X, F32), ptr(Y), ptr(Z), ptr(out, F32), n, d, alpha, beta,
-         gamma, drop_mode, p, seed, tag, stream())
+         gamma, drop_mode, p, seed, seed_tag(seed, tag), stream())
     return out
 
 
@@ -79,7 +79,7 @@ def _gather_forward(hi, E, P, seq, pos, scale, p, seed, tag):
     d = E.shape[1]
     x = torch.empty(*seq.shape, d, device=E.device, dtype=F32)
     call("c2dsr_gather_fwd", ptr(hi), ptr(E), ptr(P), ptr(seq, I64), ptr(pos, I64), ptr(x), seq.numel(),
-         d, scale, p, seed, tag, stream())
+         d, scale, p, seed, seed_tag(seed, tag), stream())
     return x
 
 
@@ -91,7 +91,7 @@ def _gather_backward(dx, seq, pos, n_rows, d, p_shape, scale, pad_idx, p, seed, 
     nb = query("c2dsr_gather_bwd_workspace_bytes", n, d, n_rows, p_shape[0])
     ws = workspace.get(nb, dx.device)
     call("c2dsr_gather_bwd", ptr(dx), ptr(seq), ptr(pos), ptr(d_hi), ptr(d_E), ptr(d_P), n, d, n_rows, p_shape[0],
-         pad_idx, scale, p, seed, tag, ptr(ws), ws.numel(), stream())
+         pad_idx, scale, p, seed, seed_tag(seed, tag), ptr(ws), ws.numel(), stream())
     return d_hi, d_E, d_P
 
 
@@ -139,8 +139,8 @@ def _encoder_forward(x, seq, w, n_head, pad_idx, norm_first, p, seed, tag, dense
     ws = workspace.get(query("c2dsr_encoder_workspace_bytes", T, d, n_head, dense_passes), x.device)
     table = _layer_table(w, n_layers)
     call("c2dsr_encoder_fwd", C.addressof(table), n_layers, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), n_seq,
-         L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, p, seed, tag, ptr(out), ptr(saved), ptr(ws),
-         ws.numel(), stream())
+         L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, p, seed, seed_tag(seed, tag), ptr(out),
+         ptr(saved), ptr(ws), ws.numel(), stream())
     return out, saved
 
 
@@ -158,7 +158,7 @@ def _encoder_backward(d_out, saved, seq, w, cfg):
     wt, gt = _layer_table(w, n_layers), _layer_table(grads, n_layers)
     call("c2dsr_encoder_bwd", C.addressof(wt), C.addressof(gt), n_layers, ptr(w[-2]), ptr(grads[-2]),
          ptr(grads[-1]), ptr(d_out), ptr(seq), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS,
-         p, seed, tag, ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
+         p, seed, seed_tag(seed, tag), ptr(saved), ptr(dx), ptr(ws), ws.numel(), stream())
     return dx, grads
 
 

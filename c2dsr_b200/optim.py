@@ -3,9 +3,10 @@
 Drop-in for ``torch.optim.AdamW(params, lr, weight_decay, amsgrad=True)`` as the reference
 builds it (trainer.py:21-22): same ``param_groups`` (so ``StepLR`` works), same update
 formulas, parameters whose ``.grad`` is None are skipped (the dead prototype-layer weights,
-SURVEY.md Q3).  Gradients are read from ``p.grad`` -- which, as in the reference, keeps
-accumulating across batches until ``zero_grad()`` is called once per epoch (Q2) -- or, for
-data-parallel runs, from a caller-supplied all-reduced copy.
+SURVEY.md Q3).  Gradients are read from ``p.grad`` or, for data-parallel runs, from a
+caller-supplied all-reduced copy.  As in the reference they accumulate across batches until
+``zero_grad()`` is called once per epoch (Q2): either in ``p.grad`` itself (``accumulate=False``,
+torch semantics) or in a sum owned by the optimiser (``accumulate=True``, see the class).
 """
 from __future__ import annotations
 
@@ -18,14 +19,54 @@ from ._cabi import AdamTensor, call, ptr, stream
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=True):
+    """``accumulate=True`` (what the Trainer uses): the optimiser owns the per-epoch gradient sum of Q2.  Each
+    step the kernel does ``grad_sum += p.grad`` itself and updates from ``grad_sum``; ``p.grad`` is then
+    released, so the next backward hands its gradient over without an add kernel per parameter (56 launches
+    and ~1 GB of traffic per step at the Food-Kitchen shape).  ``zero_grad()`` clears the sums;
+    ``accumulated_grad(p)`` returns what ``p.grad`` holds in the reference at the same point."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=True,
+                 accumulate=False):
         if not amsgrad:
             raise ValueError("FusedAdamW implements the amsgrad variant only (the reference uses amsgrad=True)")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=True))
+        self.accumulate = bool(accumulate)
         self._table_key = None
         self._table_dev = None
-        self._table_host = None
+        self._graph_tables = []   # pinned tables referenced by captured memcpy nodes: must outlive the graphs
         self.n_steps = 0          # bumped on every step(): parameters are updated through raw pointers
+        # device-resident step state (c2dsr_step_state, see the header): when attached, the step number and the
+        # learning rate are read by the kernel itself, which is what lets a whole training step be replayed
+        # from a CUDA graph.  The caller advances it with c2dsr_step_begin after every step.
+        self.dyn_state = None
+        self._dyn_lr = None
+
+    def attach_step_state(self, state: torch.Tensor):
+        if len(self.param_groups) != 1:
+            raise ValueError("the device step state carries one learning rate: use a single param group")
+        self.dyn_state = state
+        self._dyn_lr = float(self.param_groups[0]["lr"])
+        call("c2dsr_step_state_set", ptr(state), self.n_steps, self._dyn_lr, stream())
+
+    def sync_lr(self):
+        """Push a learning rate changed by the scheduler to the device state (stream-ordered, no host sync)."""
+        lr = float(self.param_groups[0]["lr"])
+        if self.dyn_state is not None and lr != self._dyn_lr:
+            call("c2dsr_step_state_set_lr", ptr(self.dyn_state), lr, stream())
+            self._dyn_lr = lr
+
+    def accumulated_grad(self, p):
+        """The gradient sum since the last zero_grad() (= ``p.grad`` of the reference); None if p never had one."""
+        if not self.accumulate:
+            return p.grad
+        return self.state[p].get("grad_sum") if p in self.state else None
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+        if self.accumulate:
+            sums = [st["grad_sum"] for st in self.state.values() if "grad_sum" in st]
+            if sums:
+                torch._foreach_zero_(sums)
 
     @torch.no_grad()
     def step(self, closure=None, grads: Optional[Dict[torch.nn.Parameter, torch.Tensor]] = None):
@@ -43,6 +84,8 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if self.accumulate:
+                        st["grad_sum"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
                 live.append((p, g, st))
             if not live:
@@ -51,25 +94,47 @@ class FusedAdamW(torch.optim.Optimizer):
             buckets = {s: [x for x in live if x[2]["step"] == s] for s in steps}   # normally a single bucket
             for s, items in buckets.items():
                 self._launch(gi, group, items, s)
+            if self.accumulate:
+                for p, _, _ in live:
+                    p.grad = None               # consumed: the next backward's gradient is taken over as is
         return loss
 
     def _launch(self, gi, group, items, step_no):
         key = (gi, step_no == 0, tuple((p.data_ptr(), g.data_ptr()) for p, g, _ in items))
         dev = items[0][0].device
-        if key != self._table_key:
+        capturing = torch.cuda.is_current_stream_capturing()
+        if key != self._table_key or capturing:
             n = len(items)
             host = (AdamTensor * n)()
             for i, (p, g, st) in enumerate(items):
                 if not (p.is_contiguous() and g.is_contiguous() and g.dtype == torch.float32):
                     raise RuntimeError("FusedAdamW needs contiguous fp32 parameters and gradients")
-                host[i].p, host[i].g, host[i].acc = ptr(p), None, ptr(g)
+                if self.accumulate:
+                    host[i].p, host[i].g, host[i].acc = ptr(p), ptr(g), ptr(st["grad_sum"])
+                else:
+                    host[i].p, host[i].g, host[i].acc = ptr(p), None, ptr(g)
                 host[i].m, host[i].v, host[i].vmax = ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), ptr(st["max_exp_avg_sq"])
                 host[i].n = p.numel()
             raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8)
-            self._table_dev = raw.to(dev)
-            self._table_key = key
+            # pinned staging + asynchronous copy: no host sync (torch's host allocator keeps the block until the
+            # copy has run); inside a stream capture the copy becomes a memcpy node that re-reads the pinned
+            # table on every replay, so that table is kept for the life of the process
+            pinned = torch.empty(raw.numel(), dtype=torch.uint8, pin_memory=True)
+            pinned.copy_(raw)
+            if capturing:
+                self._graph_tables.append(pinned)
+            table = torch.empty(raw.numel(), dtype=torch.uint8, device=dev)
+            table.copy_(pinned, non_blocking=True)
+            self._table_dev = table
+            self._table_key = None if capturing else key
             self._table_n = n
             self._table_max = max(p.numel() for p, _, _ in items)
         b1, b2 = group["betas"]
+        if self.dyn_state is not None:
+            if not torch.cuda.is_current_stream_capturing():
+                self.sync_lr()
+            call("c2dsr_adamw_amsgrad_dyn", ptr(self._table_dev), self._table_n, self._table_max, ptr(self.dyn_state),
+                 b1, b2, group["eps"], group["weight_decay"], stream())
+            return
         call("c2dsr_adamw_amsgrad", ptr(self._table_dev), self._table_n, self._table_max, float(group["lr"]), b1, b2,
              group["eps"], group["weight_decay"], step_no, stream())

@@ -16,7 +16,8 @@ from os.path import join
 
 import torch
 
-from . import dist as cdist
+from . import _cabi, dist as cdist
+from ._cabi import DynSeed, call, ptr, query, stream, workspace
 from . import ops
 from .c2dsr import C2DSR
 from .dataloader import get_dataloader
@@ -47,7 +48,7 @@ class Trainer(object):
         self.device = torch.device(args.device)
         self.model = C2DSR(args, self.adj_share, self.adj_specific).to(self.device)
         self.optimizer = FusedAdamW(filter(lambda x: x.requires_grad, self.model.parameters()), lr=args.lr,
-                                    weight_decay=args.l2, amsgrad=True)
+                                    weight_decay=args.l2, amsgrad=True, accumulate=True)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=args.lr_step, gamma=args.lr_gamma)
         self.noter = noter
         if getattr(args, "data_on_device", True):
@@ -70,6 +71,17 @@ class Trainer(object):
         self.skip_ignored = bool(getattr(args, "skip_ignored_rows", True))
         self._wsplit = {}
         self.bucket = cdist.GradBucket()
+        # per-step device state: optimiser step number, learning rate and dropout key words (header:
+        # c2dsr_step_state).  Eager and replayed steps read the same state, so they compute the same thing.
+        self.step_state = torch.zeros(query("c2dsr_step_state_bytes"), dtype=torch.uint8, device=self.device)
+        self.seed_base = (int(getattr(args, "seed", 0)) * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03 * (self.rank + 1)) \
+            & 0xFFFFFFFFFFFFFFFF
+        self.optimizer.attach_step_state(self.step_state)
+        call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
+        self.model.dyn_seed = DynSeed(self.step_state.data_ptr() + 8)
+        # whole-step CUDA graphs (single process; the data-parallel step keeps its eager all-reduce)
+        self.use_graph = bool(getattr(args, "cuda_graph", True)) and self.world_size == 1
+        self._graphs, self._warm, self._caps = {}, {}, None
 
     def _split_cache(self, weight, n0, n1):
         """bf16 (hi, lo) split of a classifier shard, refreshed whenever the weights change."""
@@ -89,8 +101,7 @@ class Trainer(object):
         sums = torch.zeros(3, device=self.device)
         t_start = time.time()
         for batch in self.trainloader:
-            self.model.convolve_graph()
-            losses = self.train_batch(batch)
+            losses = self.train_step(batch)
             sums += torch.stack(losses).detach() * (batch[0].shape[0] * self.world_size)
         loss_tr, loss_rec, loss_mi = (sums / max(self.n_tr, 1)).tolist()    # one host sync per epoch
         self.noter.log_train(loss_tr, loss_rec, loss_mi, time.time() - t_start)
@@ -124,7 +135,7 @@ class Trainer(object):
     # ------------------------------------------------------------------------------------------
     def losses(self, batch):
         """Forward part of trainer.py:91-154 -> (loss, loss_rec, loss_mi), differentiable."""
-        n_valid = self._valid_rows(batch)
+        n_valid = self._caps if self._caps is not None else self._valid_rows(batch)
         (seq_share, seq_a, seq_b, pos, pos_a, pos_b, gt_share_a, gt_share_b, gt_a, gt_b, gt_mask_a, gt_mask_b,
          seq_neg_a, seq_neg_b) = (x.to(self.device, non_blocking=True) for x in batch)
         m = self.model
@@ -192,7 +203,75 @@ class Trainer(object):
             cdist.allreduce_sum_(out)
             return out[0], out[1], out[2]
         self.optimizer.step()
+        call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())       # state of the NEXT step
         return loss.detach(), loss_rec.detach(), loss_mi.detach()
+
+    # ---- one iteration of the training loop (trainer.py:47-53), replayed from a CUDA graph ---------------
+    def train_step(self, batch):
+        """convolve_graph() + train_batch(batch).  The first two steps of a batch shape run eagerly (they
+        create the .grad buffers, optimiser state and scratch the graph will reuse); the third is captured and
+        every later one is a replay: ~300 kernel launches become one.  The loss GEMMs of the captured step run on
+        a fixed row capacity (rows beyond the batch's valid count are ignore_index rows, which contribute
+        nothing); a batch with more valid rows than that, or any other shape, takes the eager path."""
+        if not (self.use_graph and self.model.training):
+            self.model.convolve_graph()
+            return self.train_batch(batch)
+        nv = self._valid_rows(batch) if self.skip_ignored else None
+        key = (tuple(batch[0].shape), nv is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            seen = self._warm.setdefault(key, [])
+            if len(seen) >= 2 and (nv is None or min(min(x) for x in seen) > 0):
+                g = self._capture(key, batch, seen)
+            else:
+                seen.append(nv if nv is not None else (1, 1))
+        if g is None or (nv is not None and (nv[0] > g["caps"][0] or nv[1] > g["caps"][1] or min(nv) == 0)):
+            if g is not None:
+                seen = self._warm.setdefault(key, [])
+                seen.append(nv)
+                g["overflows"] += 1
+                if g["overflows"] >= 8:                                  # the capacity was a bad guess: re-capture
+                    del self._graphs[key]
+            self.model.convolve_graph()
+            return self.train_batch(batch)
+        for s, x in zip(g["static"], batch):
+            s.copy_(x, non_blocking=True)
+        self.optimizer.sync_lr()
+        g["graph"].replay()
+        _cabi.REPLAYED_LAUNCHES += g["launches"]
+        self.optimizer.n_steps += 1
+        out = g["out"].clone()
+        return out[0], out[1], out[2]
+
+    def _capture(self, key, batch, seen):
+        B, R = batch[0].shape[0], self.len_rec
+        caps = None
+        if key[1]:
+            top = [max(x[k] for x in seen) for k in (0, 1)]
+            caps = tuple(min(2 * B * R, -(-int(1.08 * t + 32) // 128) * 128) for t in top)
+        static = tuple(torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in batch)
+        for s, x in zip(static, batch):
+            s.copy_(x)
+        self.optimizer.sync_lr()
+        workspace.pinned = True            # scratch handed to a graph must never be freed by a later regrow
+        # the cached propagations hold the previous step's autograd graph, and through it the AccumulateGrad
+        # nodes of the embedding tables, which are tied to the (legacy default) stream they were created on:
+        # drop them so that the capture builds its own
+        self.model.hi_share = self.model.hi_a = self.model.hi_b = None
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        l0 = _cabi.launch_count()
+        self._caps = caps
+        try:
+            with torch.cuda.graph(graph):
+                self.model.convolve_graph()
+                out = torch.stack(self.train_batch(static))
+        finally:
+            self._caps = None
+        g = dict(graph=graph, static=static, out=out, caps=caps or (2 * B * R, 2 * B * R),
+                 launches=_cabi.launch_count() - l0, overflows=0)
+        self._graphs[key] = g
+        return g
 
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -231,6 +231,29 @@ typedef struct {
 int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ---- per-step device state (CUDA-graph replay of a whole training step) ------------------------
+ * A captured step cannot take fresh scalars from the host, so the three things that change every step
+ * live in a small device struct: the step number and learning rate (bias corrections and step size of
+ * c2dsr_adamw_amsgrad_dyn) and two dropout key words.  Any entry point that takes (seed, tag) accepts
+ * tag | C2DSR_SEED_INDIRECT, meaning ``seed`` is the device address of c2dsr_step_state.key: the mask
+ * key is then hash(tag) XOR those words, read by the kernels themselves.
+ *   c2dsr_step_begin:  step += 1;  key = hash(step, seed_base)      (call once after every optimiser step)
+ * The eager path uses the same entries, so a replayed step and an eager one compute the same thing. */
+typedef struct {
+    uint64_t step;       /* optimiser step the next c2dsr_adamw_amsgrad_dyn call will apply */
+    uint32_t key[2];     /* per-step dropout key words (offset 8) */
+    float lr;
+    float reserved[3];
+} c2dsr_step_state;
+#define C2DSR_SEED_INDIRECT (1ull << 63)
+#define C2DSR_STEP_KEY_OFFSET 8
+int c2dsr_step_state_bytes(void);
+int c2dsr_step_state_set(void* state, int64_t step, float lr, void* stream);
+int c2dsr_step_state_set_lr(void* state, float lr, void* stream);
+int c2dsr_step_begin(void* state, uint64_t seed_base, void* stream);
+int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, const void* state,
+                            float beta1, float beta2, float eps, float weight_decay, void* stream);
+
 /* elementwise glue: out = a*x + b*y (y may be NULL) */
 int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);
 

@@ -19,8 +19,7 @@ ds.to(dev)
 tb = list(loader)
 tr.model.train(); tr.optimizer.zero_grad()
 def step(i):
-    tr.model.convolve_graph()
-    tr.train_batch(tb[i % len(tb)])
+    tr.train_step(tb[i % len(tb)])
 for i in range(3): step(i)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
@@ -37,5 +36,11 @@ tot = sum(v[1] for v in agg.values())
 print("total device-busy us/step (sum over streams):", tot / N)
 t0 = min(e.time_range.start for e in ev); t1 = max(e.time_range.end for e in ev)
 print("span us/step:", (t1 - t0) / N)
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+by_stream = {}
+for e in ev:
+    by_stream.setdefault(getattr(e, "device_resource_id", getattr(e, "device_index", 0)), [0, 0.0])
+    by_stream[getattr(e, "device_resource_id", getattr(e, "device_index", 0))][0] += 1
+    by_stream[getattr(e, "device_resource_id", getattr(e, "device_index", 0))][1] += e.device_time
+print("per-stream busy us/step:", {k: (v[0] / N, round(v[1] / N, 1)) for k, v in by_stream.items()})
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k}")
