@@ -429,69 +429,98 @@ static AttnShape make_shape(int64_t n_seq, int L, int d, int H, int64_t pad) {
     AttnShape sh{n_seq, L, d, H, d / H, pad, 1.f / sqrtf((float)(d / H))};
     return sh;
 }
-// ---- one CTA per (sequence, head): Q, K, V (and dO, O) staged in shared memory ------------------------------
-// Short sequences (L * head_dim * 5 floats <= 160 KB) take this path: every global element is read once,
-// coalesced; all dot products run out of shared memory; sums over keys / queries have a fixed order.
-constexpr int kSeqThreads = 128;
+// ---- one CTA per (sequence, head): Q, K, V (and dO) staged in shared memory ---------------------------------
+// Short sequences (the staged tiles fit in kSeqSmemLimit and head_dim % 4 == 0) take this path.  Every global
+// element is read once with 16-byte accesses; the work is cut into three block-wide phases so that no
+// phase has a serial dependency longer than one dot product:
+//   1. all (query, key) scores at once, one warp per pair (16-byte shared loads, one shuffle reduction);
+//   2. soft-max per query row (one warp per row) -> probabilities (with the dropout mask folded in);
+//   3. outputs as small dense products, one thread per float4 of output, coefficients broadcast.
+// Sums over keys / queries run in index order, so results are reproducible.
+constexpr int kSeqThreads = 256;
 constexpr int kSeqSmemLimit = 160 * 1024;
 
-__device__ __forceinline__ float smem_dot(const float* a, const float* b, int dh, int lane) {
+__device__ __forceinline__ float smem_dot4(const float* a, const float* b, int dh, int lane) {
     float s = 0.f;
-    for (int e = lane; e < dh; e += 32) s += a[e] * b[e];
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int e = lane; e < (dh >> 2); e += 32) {
+        const float4 x = a4[e], y = b4[e];
+        s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
     return warp_sum(s);
+}
+
+// copy rows [L, dh] of one head out of a [*, ld] global matrix into contiguous shared memory
+__device__ __forceinline__ void stage_rows(float* dst, const float* src, int64_t ld, int L, int dh) {
+    const int q = dh >> 2;
+    for (int idx = threadIdx.x; idx < L * q; idx += blockDim.x) {
+        const int i = idx / q, e = idx - i * q;
+        reinterpret_cast<float4*>(dst)[idx] = __ldg(reinterpret_cast<const float4*>(src + i * ld) + e);
+    }
 }
 
 __global__ void __launch_bounds__(kSeqThreads)
 attn_seq_fwd_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ seq, AttnShape sh, Dropout dr,
                     float* __restrict__ o, float* __restrict__ lse) {
-    extern __shared__ float sm[];
-    const int L = sh.L, dh = sh.dh;
+    extern __shared__ __align__(16) float sm[];
+    const int L = sh.L, dh = sh.dh, LS = L + 1;
     float* Q = sm;
     float* K = Q + L * dh;
     float* V = K + L * dh;
-    int* allow = reinterpret_cast<int*>(V + L * dh);
+    float* S = V + L * dh;                       // [L][L + 1] scores, then probabilities
+    int* allow = reinterpret_cast<int*>(S + L * LS);
     const int64_t b = blockIdx.x / sh.H;
     const int h = blockIdx.x % sh.H;
     const int64_t ld = 3 * (int64_t)sh.d;
-    for (int idx = threadIdx.x; idx < L * dh; idx += blockDim.x) {
-        const int i = idx / dh, e = idx % dh;
-        const float* row = qkv + (b * L + i) * ld + h * dh + e;
-        Q[idx] = row[0];
-        K[idx] = row[sh.d];
-        V[idx] = row[2 * sh.d];
-    }
+    const float* base = qkv + b * L * ld + h * dh;
+    stage_rows(Q, base, ld, L, dh);
+    stage_rows(K, base + sh.d, ld, L, dh);
+    stage_rows(V, base + 2 * sh.d, ld, L, dh);
     for (int j = threadIdx.x; j < L; j += blockDim.x) allow[j] = seq[b * L + j] == sh.pad;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nper = (dh + 31) >> 5;
+    // 1. scores
+    for (int p = warp; p < L * L; p += nw) {
+        const int i = p / L, j = p - i * L;
+        if (j > i || !allow[j]) continue;                                  // warp-uniform
+        const float s = smem_dot4(Q + i * dh, K + j * dh, dh, lane) * sh.scale;
+        if (lane == 0) S[i * LS + j] = s;
+    }
+    __syncthreads();
+    // 2. soft-max rows: S <- p_ij * keep_ij, 0 for masked pairs; rows with no allowed key are all zero
     for (int i = warp; i < L; i += nw) {
-        float acc[kMaxPerLane];
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) acc[k] = 0.f;
-        float m = -INFINITY, l = 0.f;
-        for (int j = 0; j <= i; ++j) {
-            if (!allow[j]) continue;
-            const float s = smem_dot(Q + i * dh, K + j * dh, dh, lane) * sh.scale;
-            const float m_new = fmaxf(m, s);
-            const float corr = expf(m - m_new);
-            const float pe = expf(s - m_new);
-            l = l * corr + pe;
-            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
-#pragma unroll
-            for (int k = 0; k < kMaxPerLane; ++k) {
-                const int e = lane + 32 * k;
-                if (k < nper && e < dh) acc[k] = acc[k] * corr + pe * keep * V[j * dh + e];
-            }
-            m = m_new;
-        }
+        float m = -INFINITY;
+        for (int j = lane; j <= i; j += 32)
+            if (allow[j]) m = fmaxf(m, S[i * LS + j]);
+        m = warp_max(m);
+        float l = 0.f;
+        for (int j = lane; j <= i; j += 32)
+            if (allow[j]) l += expf(S[i * LS + j] - m);
+        l = warp_sum(l);
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        const int64_t ti = b * L + i;
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) {
-            const int e = lane + 32 * k;
-            if (k < nper && e < dh) o[ti * sh.d + h * dh + e] = acc[k] * inv;
+        for (int j = lane; j < L; j += 32) {
+            float pr = 0.f;
+            if (j <= i && allow[j])
+                pr = expf(S[i * LS + j] - m) * inv * drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
+            S[i * LS + j] = pr;
         }
-        if (lane == 0) lse[ti * sh.H + h] = l > 0.f ? m + logf(l) : INFINITY;
+        if (lane == 0) lse[(b * L + i) * sh.H + h] = l > 0.f ? m + logf(l) : INFINITY;
+    }
+    __syncthreads();
+    // 3. O = P V
+    const int q = dh >> 2;
+    for (int idx = threadIdx.x; idx < L * q; idx += blockDim.x) {
+        const int i = idx / q, e = idx - i * q;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j <= i; ++j) {
+            const float pr = S[i * LS + j];
+            if (pr != 0.f) {
+                const float4 v = reinterpret_cast<const float4*>(V + j * dh)[e];
+                acc.x += pr * v.x; acc.y += pr * v.y; acc.z += pr * v.z; acc.w += pr * v.w;
+            }
+        }
+        reinterpret_cast<float4*>(o + (b * L + i) * sh.d + h * dh)[e] = acc;
     }
 }
 
@@ -499,110 +528,111 @@ __global__ void __launch_bounds__(kSeqThreads)
 attn_seq_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, const float* __restrict__ lse,
                     const float* __restrict__ d_o, const int64_t* __restrict__ seq, AttnShape sh, Dropout dr,
                     float* __restrict__ d_qkv) {
-    extern __shared__ float sm[];
-    const int L = sh.L, dh = sh.dh;
+    extern __shared__ __align__(16) float sm[];
+    const int L = sh.L, dh = sh.dh, LS = L + 1;
     float* Q = sm;
     float* K = Q + L * dh;
     float* V = K + L * dh;
     float* dO = V + L * dh;
-    float* O = dO + L * dh;
-    float* Pk = O + L * dh;            // [L][L]  p_ij * keep_ij          (for dV)
-    float* dS = Pk + L * L;            // [L][L]  dS_ij * scale           (for dK)
-    int* allow = reinterpret_cast<int*>(dS + L * L);
+    float* Pk = dO + L * dh;           // [L][L + 1]  p_ij * keep_ij          (for dV)
+    float* dS = Pk + L * LS;           // [L][L + 1]  dS_ij * scale           (for dQ, dK)
+    float* D = dS + L * LS;            // [L]  dO_i . O_i
+    int* allow = reinterpret_cast<int*>(D + L);
     const int64_t b = blockIdx.x / sh.H;
     const int h = blockIdx.x % sh.H;
     const int64_t ld = 3 * (int64_t)sh.d;
-    for (int idx = threadIdx.x; idx < L * dh; idx += blockDim.x) {
-        const int i = idx / dh, e = idx % dh;
-        const int64_t t = b * L + i;
-        const float* row = qkv + t * ld + h * dh + e;
-        Q[idx] = row[0];
-        K[idx] = row[sh.d];
-        V[idx] = row[2 * sh.d];
-        dO[idx] = d_o[t * sh.d + h * dh + e];
-        O[idx] = o[t * sh.d + h * dh + e];
-    }
+    const float* base = qkv + b * L * ld + h * dh;
+    stage_rows(Q, base, ld, L, dh);
+    stage_rows(K, base + sh.d, ld, L, dh);
+    stage_rows(V, base + 2 * sh.d, ld, L, dh);
+    stage_rows(dO, d_o + b * L * sh.d + h * dh, sh.d, L, dh);
     for (int j = threadIdx.x; j < L; j += blockDim.x) allow[j] = seq[b * L + j] == sh.pad;
-    for (int idx = threadIdx.x; idx < 2 * L * L; idx += blockDim.x) Pk[idx] = 0.f;
+    for (int idx = threadIdx.x; idx < 2 * L * LS; idx += blockDim.x) Pk[idx] = 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int nper = (dh + 31) >> 5;
-    // phase 1: per query i -> dq_i, and the (i, j) coefficients
+    const int q = dh >> 2;
+    // 0. D_i = dO_i . O_i  (O straight from global memory: it is used nowhere else)
     for (int i = warp; i < L; i += nw) {
-        float g[kMaxPerLane];
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) g[k] = 0.f;
-        const float D = smem_dot(dO + i * dh, O + i * dh, dh, lane);
-        const float lse_i = lse[(b * L + i) * sh.H + h];
-        for (int j = 0; j <= i; ++j) {
-            if (!allow[j]) continue;
-            const float s = smem_dot(Q + i * dh, K + j * dh, dh, lane) * sh.scale;
-            const float p = expf(s - lse_i);
-            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
-            const float dP = smem_dot(dO + i * dh, V + j * dh, dh, lane) * keep;
-            const float ds = p * (dP - D) * sh.scale;
-            if (lane == 0) {
-                Pk[i * L + j] = p * keep;
-                dS[i * L + j] = ds;
-            }
-#pragma unroll
-            for (int k = 0; k < kMaxPerLane; ++k) {
-                const int e = lane + 32 * k;
-                if (k < nper && e < dh) g[k] += ds * K[j * dh + e];
-            }
+        const float4* o4 = reinterpret_cast<const float4*>(o + (b * L + i) * sh.d + h * dh);
+        const float4* g4 = reinterpret_cast<const float4*>(dO + i * dh);
+        float s = 0.f;
+        for (int e = lane; e < q; e += 32) {
+            const float4 x = __ldg(o4 + e), y = g4[e];
+            s += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
         }
-        const int64_t ti = b * L + i;
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) {
-            const int e = lane + 32 * k;
-            if (k < nper && e < dh) d_qkv[ti * ld + h * dh + e] = g[k];
+        s = warp_sum(s);
+        if (lane == 0) D[i] = s;
+    }
+    __syncthreads();
+    // 1. per (query, key) coefficients
+    for (int p = warp; p < L * L; p += nw) {
+        const int i = p / L, j = p - i * L;
+        if (j > i || !allow[j]) continue;                                  // warp-uniform
+        float s = 0.f, t = 0.f;
+        const float4* q4 = reinterpret_cast<const float4*>(Q + i * dh);
+        const float4* k4 = reinterpret_cast<const float4*>(K + j * dh);
+        const float4* g4 = reinterpret_cast<const float4*>(dO + i * dh);
+        const float4* v4 = reinterpret_cast<const float4*>(V + j * dh);
+        for (int e = lane; e < q; e += 32) {
+            const float4 a = q4[e], c = k4[e], g = g4[e], v = v4[e];
+            s += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+            t += g.x * v.x + g.y * v.y + g.z * v.z + g.w * v.w;
+        }
+        s = warp_sum(s) * sh.scale;
+        t = warp_sum(t);
+        if (lane == 0) {
+            const float pr = expf(s - lse[(b * L + i) * sh.H + h]);
+            const float keep = drop_scale(dr, (uint64_t)((b * sh.H + h) * L + i) * L + j);
+            Pk[i * LS + j] = pr * keep;
+            dS[i * LS + j] = pr * (t * keep - D[i]) * sh.scale;
         }
     }
     __syncthreads();
-    // phase 2: per key j -> dk_j, dv_j (zero rows for keys that are never attended)
-    for (int j = warp; j < L; j += nw) {
-        float gk[kMaxPerLane], gv[kMaxPerLane];
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) gk[k] = gv[k] = 0.f;
-        if (allow[j]) {
-            for (int i = j; i < L; ++i) {
-                const float ds = dS[i * L + j], pk = Pk[i * L + j];
-#pragma unroll
-                for (int k = 0; k < kMaxPerLane; ++k) {
-                    const int e = lane + 32 * k;
-                    if (k < nper && e < dh) {
-                        gk[k] += ds * Q[i * dh + e];
-                        gv[k] += pk * dO[i * dh + e];
-                    }
+    // 2. dQ_i = sum_j dS_ij K_j ;  dK_j = sum_i dS_ij Q_i ;  dV_j = sum_i Pk_ij dO_i
+    for (int idx = threadIdx.x; idx < 3 * L * q; idx += blockDim.x) {
+        const int which = idx / (L * q), rem = idx - which * (L * q);
+        const int r = rem / q, e = rem - r * q;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (which == 0) {
+            for (int j = 0; j <= r; ++j) {
+                const float c = dS[r * LS + j];
+                if (c != 0.f) {
+                    const float4 x = reinterpret_cast<const float4*>(K + j * dh)[e];
+                    acc.x += c * x.x; acc.y += c * x.y; acc.z += c * x.z; acc.w += c * x.w;
+                }
+            }
+        } else {
+            const float* coef = which == 1 ? dS : Pk;
+            const float* src = which == 1 ? Q : dO;
+            for (int i = r; i < L; ++i) {
+                const float c = coef[i * LS + r];
+                if (c != 0.f) {
+                    const float4 x = reinterpret_cast<const float4*>(src + i * dh)[e];
+                    acc.x += c * x.x; acc.y += c * x.y; acc.z += c * x.z; acc.w += c * x.w;
                 }
             }
         }
-        const int64_t tj = b * L + j;
-#pragma unroll
-        for (int k = 0; k < kMaxPerLane; ++k) {
-            const int e = lane + 32 * k;
-            if (k < nper && e < dh) {
-                d_qkv[tj * ld + sh.d + h * dh + e] = gk[k];
-                d_qkv[tj * ld + 2 * sh.d + h * dh + e] = gv[k];
-            }
-        }
+        reinterpret_cast<float4*>(d_qkv + (b * L + r) * ld + which * sh.d + h * dh)[e] = acc;
     }
 }
 
 static int seq_smem_bytes(const AttnShape& sh, bool bwd) {
-    return ((bwd ? 5 : 3) * sh.L * sh.dh + (bwd ? 2 * sh.L * sh.L : 0) + sh.L) * 4;
+    return ((bwd ? 4 : 3) * sh.L * sh.dh + (bwd ? 2 : 1) * sh.L * (sh.L + 1) + 2 * sh.L + 8) * 4;
+}
+static bool seq_path_ok(const AttnShape& sh, bool bwd) {
+    return seq_smem_bytes(sh, bwd) <= kSeqSmemLimit && sh.dh % 4 == 0 && sh.d % 4 == 0;
 }
 
 static int launch_attn_fwd(const float* qkv, const int64_t* seq, AttnShape sh, Dropout dr, float* o, float* lse,
                            cudaStream_t st) {
-    const int smem = seq_smem_bytes(sh, false);
-    if (smem <= kSeqSmemLimit) {
+    if (seq_path_ok(sh, false) && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(attn_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemLimit);
             attr = true;
         }
-        attn_seq_fwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, smem, st>>>(qkv, seq, sh, dr, o, lse);
+        attn_seq_fwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, seq_smem_bytes(sh, false), st>>>(qkv, seq, sh, dr,
+                                                                                                        o, lse);
     } else {
         const int64_t warps = sh.n_seq * sh.H * sh.L;
         attn_fwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, seq, sh, dr, o, lse);
@@ -612,14 +642,15 @@ static int launch_attn_fwd(const float* qkv, const int64_t* seq, AttnShape sh, D
 }
 static int launch_attn_bwd(const float* qkv, const float* o, const float* lse, const float* d_o, const int64_t* seq,
                            AttnShape sh, Dropout dr, float* d_qkv, cudaStream_t st) {
-    const int smem = seq_smem_bytes(sh, true);
-    if (smem <= kSeqSmemLimit) {
+    if (seq_path_ok(sh, true) && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o) |
+                                   reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(d_qkv)) & 15) == 0) {
         static bool attr = false;
         if (!attr) {
             cudaFuncSetAttribute(attn_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeqSmemLimit);
             attr = true;
         }
-        attn_seq_bwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, smem, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
+        attn_seq_bwd_kernel<<<(unsigned)(sh.n_seq * sh.H), kSeqThreads, seq_smem_bytes(sh, true), st>>>(
+            qkv, o, lse, d_o, seq, sh, dr, d_qkv);
     } else {
         const int64_t warps = 2 * sh.n_seq * sh.H * sh.L;
         attn_bwd_kernel<<<(unsigned)ceil_div(warps, 8), 256, 0, st>>>(qkv, o, lse, d_o, seq, sh, dr, d_qkv);
@@ -639,20 +670,22 @@ static unsigned ew_blocks(int64_t n) {
 struct LayerSaved {
     float *xin, *qkv, *lse, *o, *s1, *st1, *x1, *fd, *s2, *st2;
 };
-static int64_t layer_floats(int64_t T, int d, int H) { return T * (9 * (int64_t)d + H + 4); }
+// every sub-array starts on a 16-byte boundary (float4 access) whatever the token count
+static int64_t pad4(int64_t n) { return (n + 3) & ~(int64_t)3; }
+static int64_t layer_floats(int64_t T, int d, int H) { return 9 * pad4(T * d) + pad4(T * H) + 2 * pad4(T * 2); }
 static LayerSaved carve(float* base, int64_t T, int d, int H) {
     LayerSaved s;
     float* p = base;
-    s.xin = p; p += T * d;
-    s.qkv = p; p += T * 3 * d;
-    s.lse = p; p += T * H;
-    s.o = p; p += T * d;
-    s.s1 = p; p += T * d;
-    s.st1 = p; p += T * 2;
-    s.x1 = p; p += T * d;
-    s.fd = p; p += T * d;
-    s.s2 = p; p += T * d;
-    s.st2 = p; p += T * 2;
+    s.xin = p; p += pad4(T * d);
+    s.qkv = p; p += 3 * pad4(T * d);
+    s.lse = p; p += pad4(T * H);
+    s.o = p; p += pad4(T * d);
+    s.s1 = p; p += pad4(T * d);
+    s.st1 = p; p += pad4(T * 2);
+    s.x1 = p; p += pad4(T * d);
+    s.fd = p; p += pad4(T * d);
+    s.s2 = p; p += pad4(T * d);
+    s.st2 = p; p += pad4(T * 2);
     return s;
 }
 
