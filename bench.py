@@ -37,7 +37,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", type=str, default="fk", choices=sorted(WORKLOADS))
@@ -437,8 +437,12 @@ def run_reference(a):
     out = {"impl": "reference", "metric": "train_seqs_per_sec", "value": cb["value"], "unit": "seq/s",
            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(1e3 * hp.batch_size / cb["value"], 2),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"C2DSR {hp.dataset} shape, d={hp.d_latent}, L={hp.len_max}, batch {hp.batch_size}, "
-                                  "CPU oracle port of the reference's train step + full-itemset eval"},
+           "config": {"workload": f"C2DSR {hp.dataset} shape, d={hp.d_latent}, L={hp.len_max}, batch {hp.batch_size}/GPU, "
+                                  "train step = convolve_graph + train_batch (fwd, bwd, AdamW-amsgrad); + full-itemset eval",
+                      "n_item_a": hp.n_item_a, "n_item_b": hp.n_item_b, "len_rec": hp.len_rec, "dropout": a.dropout,
+                      "global_batch": hp.batch_size,
+                      "implementation": "the reference's algorithm on the host CPU (oracle/c2dsr_oracle.py, plain "
+                                        "torch ops, all host threads); bounded sample of the same workload"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "eval": {"metric": "full_catalog_eval_queries_per_sec", "value": cb["eval_queries_per_sec"],

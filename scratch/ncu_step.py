@@ -17,6 +17,7 @@ loader = BatchLoader(ds, hp.batch_size, len_rec=hp.len_rec, ignore=(hp.n_item_a,
 tr = Trainer.from_parts(hp, bench.Quiet(), (loader, None, None), adj[0], adj[1])
 ds.to(dev)
 tb = list(loader)
+tr.use_graph = False
 tr.model.train(); tr.optimizer.zero_grad()
 def step(i):
     tr.model.convolve_graph()
