@@ -49,6 +49,7 @@ FLAGS = [
     ("--encoder_tc_passes", dict(type=int, default=3, choices=[0, 1, 3],
                                  help="encoder projections while training: 0 = fp32 FFMA, 1 / 3 = tcgen05")),
     ("--skip_ignored_rows", dict(type=int, default=1, help="0: run the loss GEMMs on ignore_index rows too")),
+    ("--cuda_graph", dict(type=int, default=1, help="0: launch every kernel of a training step eagerly")),
 ]
 
 
