@@ -115,6 +115,7 @@ class C2DSR(nn.Module):
         self.branch_streams = bool(getattr(args, "branch_streams", True))
         self._side = None
         self.dyn_seed = None
+        self._gcn_rec = {}
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
 
@@ -140,6 +141,14 @@ class C2DSR(nn.Module):
         self.hi_share = self.gnn_share(self.embed_i.weight, self.graph_share, s, 1)
         self.hi_a = self.gnn_a(self.embed_i_a.weight, self.graph_specific, s, 2)
         self.hi_b = self.gnn_b(self.embed_i_b.weight, self.graph_specific, s, 3)
+        # what a branch needs to continue its backward through the propagation itself (ops.gcn_backward)
+        self._gcn_rec = {}
+        if torch.is_grad_enabled():
+            for hi, gnn, graph, tag in ((self.hi_share, self.gnn_share, self.graph_share, 1),
+                                        (self.hi_a, self.gnn_a, self.graph_specific, 2),
+                                        (self.hi_b, self.gnn_b, self.graph_specific, 3)):
+                if gnn.n_gnn >= 1 and hi.requires_grad:
+                    self._gcn_rec[id(hi)] = (graph, gnn.n_gnn, gnn.dropout_gnn if gnn.training else 0.0, s, tag)
 
     def _branch(self, attn: SelfAttention, table: nn.Embedding, hi, seq, pos, seed: int, tag: int):
         p = attn.p if self.training else 0.0
@@ -193,6 +202,12 @@ class C2DSR(nn.Module):
                               p=attn.p if self.training else 0.0, seed=seed, gather_tag=tag * 2 + 1,
                               encoder_tag=tag * 2, n_head=attn.n_head, norm_first=attn.norm_first,
                               dense_passes=attn.dense_passes if grad else attn.dense_passes_eval, n_w=len(w)))
+            # hi = GCN(table) of this step: hand the branch the recipe and a detached hi, so that the GCN
+            # backward runs inside the branch (on its stream, with the direct-lookup gradient folded in)
+            rec = self._gcn_rec.get(id(hi)) if grad else None
+            if rec is not None and table.weight.requires_grad:
+                specs[-1]["gcn"] = rec
+                hi = hi.detach()
             flat += [hi, table.weight, attn.pos_emb.weight, *w]
         return ops.BranchSetFn.apply(specs, (None, *self._side[:len(branches) - 1]), *flat)
 

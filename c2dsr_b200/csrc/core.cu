@@ -77,13 +77,25 @@ __global__ void colsum_partial_kernel(const float* __restrict__ X, int64_t ldx, 
         partial[(int64_t)blockIdx.y * N + c] = t;
     }
 }
+// block (32, 8): row group y adds chunks y, y + 8, ... of column x, then the 8 group sums are added in group
+// order -- a fixed order, and 8 x shorter dependent chains than one thread per column
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int64_t n_chunks, int64_t N,
                                     float* __restrict__ out, int accumulate) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
+    __shared__ float part[8][33];
+    const int64_t c = (int64_t)blockIdx.x * 32 + threadIdx.x;
     float s = 0.f;
-    for (int64_t k = 0; k < n_chunks; ++k) s += partial[k * N + c];
-    out[c] = accumulate ? out[c] + s : s;
+    if (c < N) {
+#pragma unroll 4
+        for (int64_t k = threadIdx.y; k < n_chunks; k += 8) s += partial[k * N + c];
+    }
+    part[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += part[g][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
 }
 
 int colsum_dispatch(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, int accumulate, void* ws,
@@ -93,7 +105,8 @@ int colsum_dispatch(const float* X, int64_t ldx, int64_t M, int64_t N, float* ou
     if (ws && n_chunks > 1 && n_chunks * N * 4 <= ws_bytes) {
         colsum_partial_kernel<<<dim3((unsigned)ceil_div(N, 32), (unsigned)n_chunks), dim3(32, 8), 0, st>>>(
             X, ldx, M, N, (float*)ws);
-        colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>((const float*)ws, n_chunks, N, out, accumulate);
+        colsum_final_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, st>>>((const float*)ws, n_chunks, N, out,
+                                                                            accumulate);
         note_launches(2);
     } else {
         colsum_kernel<<<(unsigned)ceil_div(N, 32), dim3(32, 8), 0, st>>>(X, ldx, M, N, out, accumulate);

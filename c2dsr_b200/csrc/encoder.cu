@@ -194,16 +194,31 @@ __global__ void ln_param_partial_kernel(const float* __restrict__ d_out, const f
         part[((int64_t)blockIdx.y * 2 + 1) * d + f] = c;
     }
 }
+// block (32, 8): group y adds chunks y, y + 8, ...; the 8 group sums are added in group order (fixed order)
 __global__ void ln_param_final_kernel(const float* __restrict__ part, int64_t n_chunks, int d, float* d_w, float* d_b) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= d) return;
+    __shared__ float pw[8][33], pb[8][33];
+    const int f = blockIdx.x * 32 + threadIdx.x;
     float a = 0.f, c = 0.f;
-    for (int64_t k = 0; k < n_chunks; ++k) {
-        a += part[(k * 2) * d + f];
-        c += part[(k * 2 + 1) * d + f];
+    if (f < d) {
+#pragma unroll 4
+        for (int64_t k = threadIdx.y; k < n_chunks; k += 8) {
+            a += part[(k * 2) * d + f];
+            c += part[(k * 2 + 1) * d + f];
+        }
     }
-    d_w[f] += a;
-    d_b[f] += c;
+    pw[threadIdx.y][threadIdx.x] = a;
+    pb[threadIdx.y][threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.y == 0 && f < d) {
+        float ta = 0.f, tc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            ta += pw[g][threadIdx.x];
+            tc += pb[g][threadIdx.x];
+        }
+        d_w[f] += ta;
+        d_b[f] += tc;
+    }
 }
 
 // out = in * dropout mask (same index space as the forward site)
@@ -417,7 +432,7 @@ static int launch_ln_param(void* ws, const float* d_out, const float* s, const f
         float* part = (float*)ws;
         ln_param_partial_kernel<<<dim3((unsigned)ceil_div(d, 32), (unsigned)n_chunks), dim3(32, 8), 0, st>>>(
             d_out, s, stats, part, n_tok, d);
-        ln_param_final_kernel<<<(unsigned)ceil_div(d, 128), 128, 0, st>>>(part, n_chunks, d, d_w, d_b);
+        ln_param_final_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(part, n_chunks, d, d_w, d_b);
         note_launches(2);
     } else {
         ln_param_grad_kernel<<<(unsigned)ceil_div(d, 32), dim3(32, 8), 0, st>>>(d_out, s, stats, d_w, d_b, n_tok, d);

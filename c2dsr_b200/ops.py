@@ -62,14 +62,25 @@ class GCNFn(torch.autograd.Function):
         d_hi = _f(d_hi)
         if k == 0:
             return d_hi, None, None, None, None, None
-        c = 1.0 / (k + 1)
-        # g_{j-1} = c d_hi + m_j .* (A^T g_j), g_k = c d_hi
-        cur = spmm(g.bwd, d_hi, Y=d_hi, alpha=c, beta=c, drop_mode=2, p=p, seed=seed,
-                   tag=tag * 16 + k)
-        for j in range(k - 1, 0, -1):
-            cur = spmm(g.bwd, cur, Y=d_hi, alpha=1.0, beta=c, drop_mode=2, p=p, seed=seed,
-                       tag=tag * 16 + j)
-        return cur, None, None, None, None, None
+        return gcn_backward(g, d_hi, k, p, seed, tag), None, None, None, None, None
+
+
+def gcn_backward(g, d_hi, k: int, p: float, seed: int, tag: int, direct: bool = False, pad_idx: int = -1):
+    """Gradient w.r.t. E of hi = GCN(E) (k >= 1 hops) given d_hi:  g_k = c d_hi,  g_{j-1} = c d_hi + m_j .* (A^T g_j).
+    ``direct=True`` folds in the gradient of the branch's direct look-up E[seq] as well, which equals d_hi on every
+    row except the pad row (``nn.Embedding(padding_idx)`` blocks it there): the last product then uses
+    beta = c + 1 and the pad row is corrected, so neither a second dense [N, d] gradient nor the add of the two
+    is ever materialised."""
+    c = 1.0 / (k + 1)
+    extra = 1.0 if direct else 0.0
+    cur = spmm(g.bwd, d_hi, Y=d_hi, alpha=c, beta=c + (extra if k == 1 else 0.0), drop_mode=2, p=p, seed=seed,
+               tag=tag * 16 + k)
+    for j in range(k - 1, 0, -1):
+        cur = spmm(g.bwd, cur, Y=d_hi, alpha=1.0, beta=c + (extra if j == 1 else 0.0), drop_mode=2, p=p, seed=seed,
+                   tag=tag * 16 + j)
+    if direct:
+        cur[pad_idx].sub_(d_hi[pad_idx])
+    return cur
 
 
 # ------------------------------------------------------------------------------------------------
@@ -83,9 +94,9 @@ def _gather_forward(hi, E, P, seq, pos, scale, p, seed, tag):
     return x
 
 
-def _gather_backward(dx, seq, pos, n_rows, d, p_shape, scale, pad_idx, p, seed, tag):
+def _gather_backward(dx, seq, pos, n_rows, d, p_shape, scale, pad_idx, p, seed, tag, want_dE=True):
     d_hi = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
-    d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32)
+    d_E = torch.zeros(n_rows, d, device=dx.device, dtype=F32) if want_dE else None
     d_P = torch.zeros(p_shape, device=dx.device, dtype=F32)
     n = seq.numel()
     nb = query("c2dsr_gather_bwd_workspace_bytes", n, d, n_rows, p_shape[0])
@@ -191,8 +202,10 @@ class BranchSetFn(torch.autograd.Function):
     no cross-stream bookkeeping is left to it.
 
     ``specs``: per branch a dict(seq, pos, scale, pad, p, seed, gather_tag, encoder_tag, n_head,
-    norm_first, dense_passes, n_w); ``streams``: per branch a torch.cuda.Stream or None (= the caller's
-    stream); ``flat``: per branch hi, E, P and the n_w encoder weights."""
+    norm_first, dense_passes, n_w, gcn); ``streams``: per branch a torch.cuda.Stream or None (= the caller's
+    stream); ``flat``: per branch hi, E, P and the n_w encoder weights.  ``gcn`` = (graph, n_gnn, p, seed,
+    tag) says that ``hi`` (passed detached) is GCN(E) of the same step: the backward then continues through
+    the propagation on the branch's own stream and returns the whole gradient of E (see gcn_backward)."""
 
     @staticmethod
     def forward(ctx, specs, streams, *flat):
@@ -249,9 +262,14 @@ class BranchSetFn(torch.autograd.Function):
                 cfg = (n_seq, L, d, sp["n_head"], sp["pad"], sp["norm_first"], sp["p"], sp["seed"],
                        sp["encoder_tag"], (nw - 2) // 12, sp["dense_passes"])
                 dx, grads = _encoder_backward(d_out, saved_all[slot], seq, wts[i], cfg)
+                gcn = sp.get("gcn")
                 d_hi, d_E, d_P = _gather_backward(dx, seq, pos, hi_shape[0], d, p_shape, sp["scale"], sp["pad"],
-                                                  sp["p"], sp["seed"], sp["gather_tag"])
+                                                  sp["p"], sp["seed"], sp["gather_tag"], want_dE=gcn is None)
                 del dx
+                if gcn is not None:
+                    graph, k, gp, gseed, gtag = gcn
+                    d_E = gcn_backward(graph, d_hi, k, gp, gseed, gtag, direct=True, pad_idx=sp["pad"])
+                    d_hi = None
             result[i] = [d_hi, d_E, d_P, *grads]
         for st in streams:
             if st is not None:
