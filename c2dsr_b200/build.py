@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         s, o = os.path.join(CSRC, src), os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
+            jobs.append([nvcc, *NVCC_FLAGS, *os.environ.get("C2DSR_NVCC_DEFS", "").split(), "-c", s, "-o", o]
+                        + (["-Xptxas", "-v"] if verbose else []))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -164,9 +164,24 @@ __global__ void __launch_bounds__(256) spmm_kernel(SpmmArgs a, bool skip_long) {
 // instruction instead of 32 lanes x 2 LDG.128.  The addend rows Y / Z of the group are contiguous: one bulk
 // copy each, issued before the first gather, so that finishing a row never waits on a load (in the
 // one-row-per-warp form 58 % of the stall samples sat on the Y load of finish_row).
-constexpr int kBulkWarps = 4;              // warps per CTA
-constexpr int kBulkStages = 2;
-constexpr int kBulkStageBytes = 4096;      // per warp and stage: 4096 / (4 d) gathered rows
+#ifndef C2DSR_SPMM_WARPS
+#define C2DSR_SPMM_WARPS 4
+#endif
+#ifndef C2DSR_SPMM_STAGES
+#define C2DSR_SPMM_STAGES 2
+#endif
+#ifndef C2DSR_SPMM_STAGE_BYTES
+#define C2DSR_SPMM_STAGE_BYTES 2048
+#endif
+#ifndef C2DSR_SPMM_RPW
+#define C2DSR_SPMM_RPW 2
+#endif
+constexpr int kBulkWarps = C2DSR_SPMM_WARPS;              // warps per CTA
+constexpr int kBulkStages = C2DSR_SPMM_STAGES;
+constexpr int kBulkStageBytes = C2DSR_SPMM_STAGE_BYTES;   // per warp and stage: bytes / (4 d) gathered rows, at least one
+// (measured at d = 256 on the FK graph, 4 warps: 2 stages x 2 KB, 2 rows per warp = 105 us; 4 KB stages / 4 rows
+// = 139 us; 3 stages or 8 KB stages = 170-195 us: resident warps per SM matter more than depth per warp)
+constexpr int kBulkBarBytes = (kBulkWarps * (kBulkStages + 1) * 8 + 127) / 128 * 128;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
@@ -199,9 +214,10 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + warp * (kBulkStages + 1);
     const uint32_t row_bytes = (uint32_t)a.d * 4u;
     const int n_add = (a.Y ? 1 : 0) + (a.Z ? 1 : 0);
-    const size_t per_warp = (size_t)kBulkStages * kBulkStageBytes + (size_t)n_add * RPW * row_bytes;
-    float* stage0 = reinterpret_cast<float*>(smem_raw + 128 + warp * per_warp);
-    float* ybuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage0) + kBulkStages * kBulkStageBytes);
+    const size_t stage_bytes = (size_t)chunk * row_bytes;
+    const size_t per_warp = (size_t)kBulkStages * stage_bytes + (size_t)n_add * RPW * row_bytes;
+    float* stage0 = reinterpret_cast<float*>(smem_raw + kBulkBarBytes + warp * per_warp);
+    float* ybuf = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(stage0) + kBulkStages * stage_bytes);
     float* zbuf = ybuf + (a.Y ? RPW * a.d : 0);
     const int nv = a.d >> 2;
     if (lane == 0) {
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
         if (lane == 0) bar_expect_tx(bars + s, (uint32_t)cnt * row_bytes);
         __syncwarp();
         if (lane < cnt)
-            bulk_copy_g2s(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * kBulkStageBytes + (size_t)lane * row_bytes,
+            bulk_copy_g2s(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * stage_bytes + (size_t)lane * row_bytes,
                           a.X + (int64_t)c * a.d, row_bytes, bars + s);
 #pragma unroll
         for (int t = 0; t < kBulkStages; ++t)
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
                 c_l = c_s[t];
                 v_l = v_s[t];
             }
-        const float4* st4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * kBulkStageBytes);
+        const float4* st4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * stage_bytes);
         for (int e = 0; e < cnt; ++e) {
             while (beg + e >= row_end) flush();                      // warp-uniform
             const float v = __shfl_sync(0xffffffffu, v_l, e);
@@ -372,14 +388,15 @@ extern "C" int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float
     C2DSR_REQUIRE(X != out, "spmm cannot run in place on X");
     SpmmArgs a{rowptr, col, val, X, Y, Z, out, n_rows, d, alpha, beta, gamma, drop_mode, make_dropout(p, seed, tag)};
     if (a.dr.p == 0.f) a.drop_mode = 0;
-    constexpr int kRowsPerWarp = 4;
+    constexpr int kRowsPerWarp = C2DSR_SPMM_RPW;
     const unsigned blocks = (unsigned)ceil_div(n_rows, 8 * kRowsPerWarp);
     cudaStream_t st = (cudaStream_t)stream;
     const bool split = long_rows != nullptr && n_long > 0;
     const int smem = 32 * d * 4;
     const int n_add = (Y ? 1 : 0) + (Z ? 1 : 0);
-    const int bulk_smem = 128 + kBulkWarps * (kBulkStages * kBulkStageBytes + n_add * kRowsPerWarp * d * 4);
-    const int chunk = kBulkStageBytes / (4 * d) < 32 ? kBulkStageBytes / (4 * d) : 32;
+    int chunk = kBulkStageBytes / (4 * d) < 32 ? kBulkStageBytes / (4 * d) : 32;
+    if (chunk < 1) chunk = 1;
+    const int bulk_smem = kBulkBarBytes + kBulkWarps * (kBulkStages * chunk * d * 4 + n_add * kRowsPerWarp * d * 4);
     static const char* force = getenv("C2DSR_SPMM");            // "warp" / "bulk": benchmarking override
     const bool bulk = chunk >= 1 && (d % 4) == 0 && bulk_smem <= 200 * 1024 &&
                       ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(Z)) & 15) == 0 &&
