@@ -381,9 +381,20 @@ def run_b200(a):
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(hp, adj, fields, ev, max_seconds=25.0)
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        # captured graphs hold NCCL kernels: release them before the communicator goes away, and do not let a
+        # stuck communicator teardown turn a finished measurement into a hang
+        import gc
+        tr._graphs.clear()
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Thread(target=torch.distributed.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout=20.0)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,6 +462,9 @@ def run_reference(a):
 
 
 if __name__ == "__main__":
+    if os.environ.get("C2DSR_HANG_DUMP"):          # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["C2DSR_HANG_DUMP"]), exit=True)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

@@ -79,8 +79,9 @@ class Trainer(object):
         self.optimizer.attach_step_state(self.step_state)
         call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
         self.model.dyn_seed = DynSeed(self.step_state.data_ptr() + 8)
-        # whole-step CUDA graphs (single process; the data-parallel step keeps its eager all-reduce)
-        self.use_graph = bool(getattr(args, "cuda_graph", True)) and self.world_size == 1
+        # whole-step CUDA graphs; the data-parallel step captures its NCCL all-reduces too
+        self.use_graph = bool(getattr(args, "cuda_graph", True)) and \
+            (self.world_size == 1 or bool(getattr(args, "cuda_graph_dp", True)))
         self._graphs, self._warm, self._caps = {}, {}, None
 
     def _split_cache(self, weight, n0, n1):
