@@ -4,8 +4,9 @@ box, gloo in the CPU tests).  The path has exactly two exchange steps (SURVEY.md
 * training  -- data-parallel: the global batch is split across ranks, parameters and graph are
   replicated; per step one tiny integer all-reduce (valid-target counts, so that loss
   normalisers equal the single-GPU ones) and one sum all-reduce of the fp32 gradients;
-* evaluation -- the item catalogue is sharded by rows of the classifier; the target score comes
-  from the owning shard (sum all-reduce with zeros elsewhere, exact) and the per-shard partial
+* evaluation -- each rank encodes its slice of the query batch and the query vectors are
+  all-gathered (2 MB); the item catalogue is sharded by rows of the classifier; the target score
+  comes from the owning shard (sum all-reduce with zeros elsewhere, exact) and the per-shard partial
   rank counts are summed (int32 all-reduce, order independent, bit-exact).
 """
 from __future__ import annotations
@@ -47,6 +48,20 @@ def shard_bounds(n: int, rank: int, world_size: int, align: int = 1) -> Tuple[in
     per = (per + align - 1) // align * align
     n0 = min(rank * per, n)
     return n0, min(n0 + per, n)
+
+
+def allgather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Concatenate per-rank row blocks made with ``shard_bounds(n_total, rank, world)`` back into
+    [n_total, ...] on every rank (one all-gather of equally padded blocks).  Identity for one process."""
+    rank, world_size = world()
+    if world_size == 1:
+        return local
+    per = (n_total + world_size - 1) // world_size
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((per * world_size,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    return out[:n_total]
 
 
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:

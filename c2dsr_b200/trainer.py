@@ -279,12 +279,24 @@ class Trainer(object):
     def eval_queries(self, batch):
         """q_i = h_share[i, L-1] + (hx[i, idx_last_a] | hy[i, idx_last_b])  (trainer.py:169-177, Q8)."""
         seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b, xory, gt_last, list_neg = batch
-        h_share, hx, hy = self.model(seq_share, seq_a, seq_b, pos, pos_a, pos_b)
-        B, L, _ = h_share.shape
-        ar = torch.arange(B, device=h_share.device)
-        dom_b = xory.view(-1) != 0
-        pick = torch.where(dom_b.unsqueeze(-1), hy[ar, idx_b.view(-1) % L], hx[ar, idx_a.view(-1) % L])
-        return h_share[:, -1] + pick, dom_b
+        B_all = seq_share.shape[0]
+        dom_b_all = xory.view(-1) != 0
+        # the encoders are per-sequence work: each rank encodes its slice of the batch and the query
+        # vectors are all-gathered (rows do not depend on which other rows share their launch)
+        r0, r1 = cdist.shard_bounds(B_all, self.rank, self.world_size) if self.world_size > 1 else (0, B_all)
+        seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b = (
+            x[r0:r1] for x in (seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b))
+        dom_b = dom_b_all[r0:r1]
+        B = r1 - r0
+        if B > 0:
+            h_share, hx, hy = self.model(seq_share, seq_a, seq_b, pos, pos_a, pos_b)
+            L = h_share.shape[1]
+            ar = torch.arange(B, device=h_share.device)
+            pick = torch.where(dom_b.unsqueeze(-1), hy[ar, idx_b.view(-1) % L], hx[ar, idx_a.view(-1) % L])
+            q = h_share[:, -1] + pick
+        else:
+            q = torch.zeros(0, self.d_latent, device=self.device)
+        return cdist.allgather_rows(q.contiguous(), B_all), dom_b_all
 
     @torch.no_grad()
     def rank_queries(self, q, gt, neg, weight, bias):

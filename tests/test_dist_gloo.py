@@ -31,6 +31,11 @@ def _worker(rank, world, port, ret):
     assert cdist.world() == (rank, world)
     ok = True
 
+    # --- query rows encoded per rank, all-gathered back in order (odd count: the last block is short) ---
+    full = torch.arange(37 * 3, dtype=torch.float32).view(37, 3)
+    r0, r1 = cdist.shard_bounds(37, rank, world)
+    ok &= bool(torch.equal(cdist.allgather_rows(full[r0:r1].clone(), 37), full))
+
     # --- catalogue-sharded ranking: identical on every rank, equal to the unsharded oracle ---
     rng = np.random.default_rng(0)
     n_q, N, d = 37, 1003, 16
