@@ -71,6 +71,15 @@ def preprocess_graph(args, filename: str):
             _to_sparse(normalised_coo(specific, args.n_item), args.n_item))
 
 
+def make_graph_device(args, filename: str):
+    """--device_graph: transitions from the raw log (vectorised on the host), then summed duplicates, row
+    normalisation, CSR and CSR^T on the GPU (CsrGraph.from_edges).  Returns two CsrGraph objects, which
+    C2DSR accepts in place of the reference's COO tensors.  Same arrays, bit for bit, as make_graph()."""
+    shared, specific = transition_edges(read_raw(filename), args.n_item_a)
+    return (CsrGraph.from_edges(shared, args.n_item, args.device),
+            CsrGraph.from_edges(specific, args.n_item, args.device))
+
+
 def make_graph(args, filename: str):
     """Reference signature utils/graph.py:99-109."""
     if getattr(args, "use_raw", False):
@@ -104,6 +113,41 @@ class CsrGraph:
         self.t_long_rows = self._long(self.t_rowptr)
 
     LONG_ROW = 256          # = c2dsr_spmm_long_row_threshold(): rows above it get a whole CTA in the SpMM
+
+    @classmethod
+    def from_edges(cls, edges, n: int, device):
+        """Build A = D^-1 (summed transitions) and A^T on the device straight from raw (src, dst) pairs
+        (c2dsr_graph_build: radix sort, run-length unique, bit-exact normalisation) -- the device-side
+        replacement of utils/graph.py:33-96 for large logs; same arrays as CsrGraph(adj) gives for the
+        reference's COO tensor."""
+        from ._cabi import call, ptr, query, stream
+        device = torch.device(device)
+        e = torch.as_tensor(edges)
+        src = e[:, 0].to(device=device, dtype=torch.int32).contiguous()
+        dst = e[:, 1].to(device=device, dtype=torch.int32).contiguous()
+        m = int(src.numel())
+        self = cls.__new__(cls)
+        self.n = n
+        ws = torch.empty(query("c2dsr_graph_build_workspace_bytes", m, n), dtype=torch.uint8, device=device)
+        out = []
+        for transpose in (0, 1):
+            rowptr = torch.empty(n + 1, dtype=torch.int32, device=device)
+            col = torch.empty(max(m, 1), dtype=torch.int32, device=device)
+            val = torch.empty(max(m, 1), dtype=torch.float32, device=device)
+            nnz = torch.zeros(1, dtype=torch.int32, device=device)
+            call("c2dsr_graph_build", ptr(src), ptr(dst), m, n, transpose, ptr(rowptr), ptr(col), ptr(val), ptr(nnz),
+                 ptr(ws), ws.numel(), stream())
+            k = int(nnz.item())                       # offline: one host sync per orientation
+            out.append((rowptr, col[:k].clone(), val[:k].clone()))
+        (self.rowptr, self.col, self.val), (self.t_rowptr, self.t_col, self.t_val) = out
+        self.nnz = int(self.col.numel())
+        self.long_rows = self._long(self.rowptr.cpu().long())
+        self.t_long_rows = self._long(self.t_rowptr.cpu().long())
+        for name in ("long_rows", "t_long_rows"):
+            t = getattr(self, name)
+            if t is not None:
+                setattr(self, name, t.to(device))
+        return self
 
     @classmethod
     def _long(cls, rowptr):

@@ -50,6 +50,7 @@ FLAGS = [
                                  help="encoder projections while training: 0 = fp32 FFMA, 1 / 3 = tcgen05")),
     ("--skip_ignored_rows", dict(type=int, default=1, help="0: run the loss GEMMs on ignore_index rows too")),
     ("--cuda_graph", dict(type=int, default=1, help="0: launch every kernel of a training step eagerly")),
+    ("--device_graph", dict(action="store_true", help="with --use_raw: build the adjacency CSRs on the GPU")),
 ]
 
 

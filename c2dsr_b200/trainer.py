@@ -21,7 +21,7 @@ from ._cabi import DynSeed, call, ptr, query, stream, workspace
 from . import ops
 from .c2dsr import C2DSR
 from .dataloader import get_dataloader
-from .graph import make_graph
+from .graph import make_graph, make_graph_device
 from .optim import FusedAdamW
 
 
@@ -30,7 +30,10 @@ class Trainer(object):
         self.rank, self.world_size = cdist.world()
         args.rank, args.world_size = self.rank, self.world_size
         self.trainloader, self.valloader, self.testloader = get_dataloader(args)
-        self.adj_share, self.adj_specific = make_graph(args, join(args.path_raw, 'train_new.txt'))
+        if getattr(args, "device_graph", False) and getattr(args, "use_raw", False):
+            self.adj_share, self.adj_specific = make_graph_device(args, join(args.path_raw, 'train_new.txt'))
+        else:
+            self.adj_share, self.adj_specific = make_graph(args, join(args.path_raw, 'train_new.txt'))
         self._setup(args, noter)
 
     @classmethod

@@ -231,6 +231,17 @@ typedef struct {
 int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ---- adjacency builder (utils/graph.py:33-96: preprocess_graph + normalize) -------------------
+ * Raw directed transitions (src[i] -> dst[i], duplicates allowed) to the CSR of A = D^-1 (summed counts)
+ * (transpose = 0) or of A^T (transpose = 1; values still divided by the row sum of the SOURCE item).
+ * rowptr [n_rows + 1], col / val with capacity n_edges, *nnz_out = number of distinct pairs (device int).
+ * Rows are column-sorted; val = (1 / rowsum) * count with separately rounded fp32 operations, bit-identical
+ * to the reference's normalisation.  Deterministic (LSD radix sort + scans, integer atomics only). */
+int64_t c2dsr_graph_build_workspace_bytes(int64_t n_edges, int64_t n_rows);
+int c2dsr_graph_build(const int32_t* src, const int32_t* dst, int64_t n_edges, int64_t n_rows, int transpose,
+                      int32_t* rowptr, int32_t* col, float* val, int32_t* nnz_out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
+
 /* ---- per-step device state (CUDA-graph replay of a whole training step) ------------------------
  * A captured step cannot take fresh scalars from the host, so the three things that change every step
  * live in a small device struct: the step number and learning rate (bias corrections and step size of

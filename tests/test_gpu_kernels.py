@@ -414,3 +414,24 @@ def test_adamw_amsgrad_vs_oracle():
     for i, p in enumerate(dev_p):
         assert rel_err(p.detach().cpu(), params[str(i)]) < 2e-6
     assert torch.equal(dead.detach().cpu(), torch.ones(3))
+
+
+# ------------------------------------------------------------------------------------------------
+# adjacency builder on the device vs the host path (utils/graph.py semantics)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,n_edges,seed", [(50, 0, 0), (50, 400, 1), (300, 5000, 2), (70000, 200000, 3)])
+def test_graph_build_matches_host(n, n_edges, seed):
+    from c2dsr_b200.graph import CsrGraph, _to_sparse, normalised_coo
+    rng = np.random.default_rng(seed)
+    # heavy-tailed sources / destinations with many duplicate pairs, some rows empty
+    src = np.minimum((rng.pareto(1.2, n_edges) * 3).astype(np.int64), n - 1)
+    dst = np.minimum((rng.pareto(1.0, n_edges) * 5).astype(np.int64), n - 1)
+    edges = np.stack((src, dst), 1)
+    got = CsrGraph.from_edges(edges, n, DEV)
+    ref = CsrGraph(_to_sparse(normalised_coo(edges, n), n), DEV)
+    for a, b in ((got.fwd, ref.fwd), (got.bwd, ref.bwd)):
+        assert torch.equal(a[0].cpu(), b[0].cpu())                   # rowptr
+        assert torch.equal(a[1].cpu(), b[1].cpu())                   # col (column-sorted rows)
+        assert torch.equal(a[2].cpu(), b[2].cpu())                   # val, bit for bit
+        assert (a[3] is None) == (b[3] is None) and (a[3] is None or torch.equal(a[3].cpu(), b[3].cpu()))
+    assert got.nnz == ref.nnz
