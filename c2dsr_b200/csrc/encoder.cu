@@ -795,7 +795,8 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const flo
         const LayerSaved s = carve(saved + l * lf, T, d, n_head);
         const c2dsr_layer_weights& w = layers[l];
         float* next = l + 1 < n_layers ? carve(saved + (l + 1) * lf, T, d, n_head).xin : xlast;
-        const uint64_t tb = tag * 1024 + (uint64_t)l * 8;
+        // per-layer, per-site tags; the "seed is a device pointer" flag (top bit) is carried over unchanged
+        const uint64_t tb = ((tag & ~kSeedIndirect) * 1024 + (uint64_t)l * 8) | (tag & kSeedIndirect);
         const float* attn_in = s.xin;
         if (norm_first) {
             RUN(launch_add_ln(s.xin, nullptr, w.ln1_w, w.ln1_b, nullptr, s.s1, s.st1, T, d, 1, eps, none, st));
@@ -872,7 +873,8 @@ int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads
         const LayerSaved s = carve(saved + l * lf, T, d, n_head);
         const c2dsr_layer_weights& w = layers[l];
         const c2dsr_layer_grads& gw = grads[l];
-        const uint64_t tb = tag * 1024 + (uint64_t)l * 8;
+        // per-layer, per-site tags; the "seed is a device pointer" flag (top bit) is carried over unchanged
+        const uint64_t tb = ((tag & ~kSeedIndirect) * 1024 + (uint64_t)l * 8) | (tag & kSeedIndirect);
         auto masked = [&](const float* src, uint64_t site) -> const float* {
             if (!has_drop) return src;
             drop_mul_kernel<<<ew_blocks(Td), 256, 0, st>>>(src, dy, Td, make_dropout(p, seed, tb + site));

@@ -139,6 +139,35 @@ def test_run_epoch_and_run_test_contract():
     assert all(torch.isfinite(p).all() for p in tr.model.parameters())
 
 
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_captured_step_equals_eager_step(p):
+    """Trainer.train_step replays a CUDA graph from the third step on.  Eager and replayed steps read the
+    same device step state (optimiser step number, dropout key words), so with the same batches the two
+    trainers must produce the same losses and weights (up to the summation order of the loss GEMMs, whose
+    row capacity differs) -- with dropout on as well as off."""
+    from c2dsr_b200 import _cabi
+    g = Golden("tiny_default")
+    runs = []
+    for graph in (False, True):
+        tr = _trainer_from_golden(g, dropout_gnn=p, dropout_attn=p, cuda_graph=graph)
+        tr.model.train()
+        tr.optimizer.zero_grad()
+        l0 = _cabi.launch_count()
+        losses = []
+        for s in range(7):
+            b = tuple(x.to(DEV) for x in g.train_batch(s % 3))
+            losses.append([float(x) for x in tr.train_step(b)])
+        assert bool(tr._graphs) == graph
+        runs.append((losses, {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()},
+                     _cabi.launch_count() - l0))
+    (le, we, ne), (lg, wg, ng) = runs
+    np.testing.assert_allclose(lg, le, rtol=2e-5)
+    for k in we:
+        if not k.endswith("attn_mask"):
+            assert rel_err(wg[k], we[k]) < 1e-4, k
+    assert ng > 0.9 * ne                       # replayed launches are counted
+
+
 def test_training_with_dropout_learns():
     """Dropout path sanity at the reference's default rates: loss decreases over a few epochs."""
     g = Golden("tiny_default")
