@@ -38,7 +38,8 @@ _PROTOS = {
     "c2dsr_gather_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, f32] + _DROP + [vp]),
     "c2dsr_gather_bwd_workspace_bytes": (i64, [i64, i32, i64, i32]),
     "c2dsr_gather_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, i64, f32] + _DROP + [vp, i64, vp]),
-    "c2dsr_spmm": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, i32, f32, f32, f32, i32] + _DROP + [vp]),
+    "c2dsr_spmm": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, i64, i32, f32, f32, f32, i32] + _DROP + [vp, vp, vp]),
+    "c2dsr_mark_rows": (i32, [vp, i64, i64, vp, vp]),
     "c2dsr_spmm_long_row_threshold": (i32, []),
     "c2dsr_gemm_workspace_bytes": (i64, [i64, i64, i64]),
     "c2dsr_gemm": (i32, [i32, i32, i64, i64, i64, f32, vp, i64, vp, i64, f32, vp, i64, vp, i32] + _DROP

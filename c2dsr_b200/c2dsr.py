@@ -116,6 +116,7 @@ class C2DSR(nn.Module):
         self._side = None
         self.dyn_seed = None
         self._gcn_rec = {}
+        self._gcn_lazy = None
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
 
@@ -135,9 +136,18 @@ class C2DSR(nn.Module):
         self._calls += 1
         return (self._seed + 0x9E3779B97F4A7C15 * self._calls) & 0xFFFFFFFFFFFFFFFF
 
-    def convolve_graph(self):
-        """models/C2DSR.py:59-62: cache hi_share / hi_a / hi_b (kept until the next call, Q13)."""
+    def convolve_graph(self, lazy: bool = False):
+        """models/C2DSR.py:59-62: cache hi_share / hi_a / hi_b (kept until the next call, Q13).
+        ``lazy=True`` (Trainer.train_step): only fix the step's seed; the three propagations are then computed
+        by the branches that consume them, each on its own stream, inside forward_all (and cached as usual)."""
         s = self._next_seed()
+        if lazy and self.branch_streams and torch.is_grad_enabled() and self.embed_i.weight.is_cuda \
+                and self.gnn_share.n_gnn >= 1:
+            self._gcn_lazy = s
+            self.hi_share = self.hi_a = self.hi_b = None
+            self._gcn_rec = {}
+            return
+        self._gcn_lazy = None
         self.hi_share = self.gnn_share(self.embed_i.weight, self.graph_share, s, 1)
         self.hi_a = self.gnn_a(self.embed_i_a.weight, self.graph_specific, s, 2)
         self.hi_b = self.gnn_b(self.embed_i_b.weight, self.graph_specific, s, 3)
@@ -158,6 +168,7 @@ class C2DSR(nn.Module):
 
     def forward(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b):
         """models/C2DSR.py:64-77 -> (h_share, hx, hy), each fp32 [B, L, d]."""
+        self._materialise()
         s = self._next_seed()
         if self.branch_streams and seq_share.is_cuda:
             return self._branch_set(((self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, 1),
@@ -169,6 +180,7 @@ class C2DSR(nn.Module):
 
     def forward_share(self, seq, pos):
         """models/C2DSR.py:79-85: the shared branch only (corrupted sequences)."""
+        self._materialise()
         return self._branch(self.attn_share, self.embed_i, self.hi_share, seq, pos, self._next_seed(), 4)
 
     def forward_all(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b, seq_neg_a, seq_neg_b):
@@ -180,6 +192,7 @@ class C2DSR(nn.Module):
         seq3 = torch.cat((seq_share, seq_neg_a, seq_neg_b), 0)
         pos3 = torch.cat((pos_share, pos_share, pos_share), 0)
         if not (self.branch_streams and seq_share.is_cuda):
+            self._materialise()
             h3 = self._branch(self.attn_share, self.embed_i, self.hi_share, seq3, pos3, s, 1)
             hx = self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2)
             hy = self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3)
@@ -204,10 +217,30 @@ class C2DSR(nn.Module):
                               dense_passes=attn.dense_passes if grad else attn.dense_passes_eval, n_w=len(w)))
             # hi = GCN(table) of this step: hand the branch the recipe and a detached hi, so that the GCN
             # backward runs inside the branch (on its stream, with the direct-lookup gradient folded in)
-            rec = self._gcn_rec.get(id(hi)) if grad else None
-            if rec is not None and table.weight.requires_grad:
+            rec = self._gcn_rec.get(id(hi)) if (grad and hi is not None) else None
+            if hi is None:                                   # lazy propagation (convolve_graph(lazy=True))
+                gnn, graph = self._gcn_of(tag)
+                specs[-1]["gcn"] = (graph, gnn.n_gnn, gnn.dropout_gnn if gnn.training else 0.0, self._gcn_lazy, tag)
+            elif rec is not None and table.weight.requires_grad:
                 specs[-1]["gcn"] = rec
                 hi = hi.detach()
             flat += [hi, table.weight, attn.pos_emb.weight, *w]
-        return ops.BranchSetFn.apply(specs, (None, *self._side[:len(branches) - 1]), *flat)
+        out = ops.BranchSetFn.apply(specs, (None, *self._side[:len(branches) - 1]), *flat)
+        n = len(branches)
+        if len(out) > n:                                     # the propagations computed on the way: cache them
+            self.hi_share, self.hi_a, self.hi_b = out[n:]
+            self._gcn_lazy = None
+        return out[:n]
+
+    def _gcn_of(self, tag: int):
+        return {1: (self.gnn_share, self.graph_share), 2: (self.gnn_a, self.graph_specific),
+                3: (self.gnn_b, self.graph_specific)}[tag]
+
+    def _materialise(self):
+        """A lazily deferred propagation that something other than forward_all needs: compute it now."""
+        if self._gcn_lazy is not None and self.hi_share is None:
+            s, self._gcn_lazy = self._gcn_lazy, None
+            self.hi_share = self.gnn_share(self.embed_i.weight, self.graph_share, s, 1)
+            self.hi_a = self.gnn_a(self.embed_i_a.weight, self.graph_specific, s, 2)
+            self.hi_b = self.gnn_b(self.embed_i_b.weight, self.graph_specific, s, 3)
 

@@ -29,6 +29,8 @@ struct SpmmArgs {
     float alpha, beta, gamma;
     int drop_mode;
     Dropout dr;
+    const uint8_t* out_need;   // optional [n_rows]: 0 = this output row is not wanted (left zero)
+    const uint8_t* x_nz;       // optional [n_cols]: 0 = this row of X is all zeros (its entries are skipped)
 };
 
 template <int VPL>
@@ -229,6 +231,16 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
     const int64_t r0 = ((int64_t)blockIdx.x * kBulkWarps + warp) * RPW;
     if (r0 >= a.n_rows) return;
     const int nr = a.n_rows - r0 < RPW ? (int)(a.n_rows - r0) : RPW;
+    // rows of this group that are wanted (all of them without a mask); a group with none ends here: only the
+    // rows a batch reads are propagated in a training step, ~6 % of the table at the Food-Kitchen shape
+    uint32_t need = (1u << nr) - 1u;
+    if (a.out_need) {
+        need = 0;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+            if (r < nr && a.out_need[r0 + r]) need |= 1u << r;
+        if (need == 0) return;
+    }
     const int rp = lane <= nr ? a.rowptr[r0 + lane] : 0;
     if (n_add && lane == 0) {                                  // addend rows of the whole group: contiguous
         bar_expect_tx(bars + kBulkStages, (uint32_t)(n_add * nr) * row_bytes);
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
     bool add_ready = n_add == 0;
     const int lo = __shfl_sync(0xffffffffu, rp, 0), hi = __shfl_sync(0xffffffffu, rp, nr);
     int cur = 0, row_beg = lo, row_end = __shfl_sync(0xffffffffu, rp, 1);
-    bool skip = skip_long && row_end - row_beg > kLongRow;
+    bool skip = (skip_long && row_end - row_beg > kLongRow) || !(need & 1u);
     float4 acc[VPL];
 #pragma unroll
     for (int k = 0; k < VPL; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -273,11 +285,12 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
         ++cur;
         row_beg = row_end;
         row_end = __shfl_sync(0xffffffffu, rp, cur + 1 <= nr ? cur + 1 : nr);
-        skip = skip_long && row_end - row_beg > kLongRow;
+        skip = (skip_long && row_end - row_beg > kLongRow) || !((need >> cur) & 1u);
     };
     const int n_chunks = (hi - lo + chunk - 1) / chunk;
     int c_s[kBulkStages];
     float v_s[kBulkStages];
+    uint32_t a_s[kBulkStages];                           // per stage: which entries of the chunk were fetched
     uint32_t phase = 0;                                  // bit s = parity to wait for on stage s
     auto issue = [&](int k, int s) {
         const int beg = lo + k * chunk;
@@ -288,9 +301,20 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
             c = a.col[beg + lane];
             v = a.val[beg + lane];
         }
-        if (lane == 0) bar_expect_tx(bars + s, (uint32_t)cnt * row_bytes);
+        // the row this lane's entry belongs to; entries of unwanted / long rows and of all-zero X rows are not fetched
+        int er = 0;
+#pragma unroll
+        for (int r = 1; r < RPW; ++r) {
+            const int b = __shfl_sync(0xffffffffu, rp, r);
+            if (r < nr && beg + lane >= b) er = r;
+        }
+        const int e_beg = __shfl_sync(0xffffffffu, rp, er), e_end = __shfl_sync(0xffffffffu, rp, er + 1);
+        bool act = lane < cnt && ((need >> er) & 1u) && !(skip_long && e_end - e_beg > kLongRow);
+        if (act && a.x_nz) act = a.x_nz[c] != 0;
+        const uint32_t mask = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) bar_expect_tx(bars + s, (uint32_t)__popc(mask) * row_bytes);
         __syncwarp();
-        if (lane < cnt)
+        if (act)
             bulk_copy_g2s(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * stage_bytes + (size_t)lane * row_bytes,
                           a.X + (int64_t)c * a.d, row_bytes, bars + s);
 #pragma unroll
@@ -298,6 +322,7 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
             if (t == s) {
                 c_s[t] = c;
                 v_s[t] = v;
+                a_s[t] = mask;
             }
     };
 #pragma unroll
@@ -311,18 +336,20 @@ __global__ void __launch_bounds__(32 * kBulkWarps) spmm_bulk_kernel(SpmmArgs a, 
         const int cnt = hi - beg < chunk ? hi - beg : chunk;
         int c_l = 0;
         float v_l = 0.f;
+        uint32_t act_l = 0;
 #pragma unroll
         for (int t = 0; t < kBulkStages; ++t)
             if (t == s) {
                 c_l = c_s[t];
                 v_l = v_s[t];
+                act_l = a_s[t];
             }
         const float4* st4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(stage0) + (size_t)s * stage_bytes);
         for (int e = 0; e < cnt; ++e) {
             while (beg + e >= row_end) flush();                      // warp-uniform
             const float v = __shfl_sync(0xffffffffu, v_l, e);
             const int c = __shfl_sync(0xffffffffu, c_l, e);
-            if (!skip) {
+            if (!skip && ((act_l >> e) & 1u)) {
 #pragma unroll
                 for (int q = 0; q < VPL; ++q) {
                     const int vi = lane + 32 * q;
@@ -349,6 +376,7 @@ __global__ void __launch_bounds__(1024) spmm_long_kernel(SpmmArgs a, const int32
     extern __shared__ float part[];                 // [32 warps][d]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row = long_rows[blockIdx.x];
+    if (a.out_need && !a.out_need[row]) return;               // not wanted: stays zero
     const int beg = a.rowptr[row], end = a.rowptr[row + 1];
     const int per = (end - beg + 31) / 32;
     const int w_beg = beg + warp * per < end ? beg + warp * per : end;
@@ -378,15 +406,37 @@ __global__ void __launch_bounds__(1024) spmm_long_kernel(SpmmArgs a, const int32
 
 using namespace c2dsr;
 
+__global__ void mark_rows_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t n_rows, uint8_t* __restrict__ mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int64_t k = ids[i];
+        if (k >= 0 && k < n_rows) mask[k] = 1;              // benign race: every writer stores the same value
+    }
+}
+
+extern "C" int c2dsr_mark_rows(const int64_t* ids, int64_t n, int64_t n_rows, uint8_t* mask, void* stream) {
+    C2DSR_REQUIRE(n_rows > 0 && n >= 0, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(mask, 0, n_rows, st);
+    if (n > 0) {
+        mark_rows_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ids, n, n_rows, mask);
+        note_launches(1);
+    }
+    return check_launch("mark_rows");
+}
+
 extern "C" int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* long_rows,
                           int n_long, const float* X, const float* Y, const float* Z, float* out, int64_t n_rows,
                           int d, float alpha, float beta, float gamma, int drop_mode, float p, uint64_t seed,
-                          uint64_t tag, void* stream) {
+                          uint64_t tag, const uint8_t* out_row_needed, const uint8_t* x_row_nonzero, void* stream) {
     if (n_rows <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 1024, "d must be a multiple of 4 in (0, 1024]");
     C2DSR_REQUIRE(drop_mode >= 0 && drop_mode <= 2, "drop_mode must be 0, 1 or 2");
     C2DSR_REQUIRE(X != out, "spmm cannot run in place on X");
-    SpmmArgs a{rowptr, col, val, X, Y, Z, out, n_rows, d, alpha, beta, gamma, drop_mode, make_dropout(p, seed, tag)};
+    SpmmArgs a{rowptr, col, val, X, Y, Z, out, n_rows, d, alpha, beta, gamma, drop_mode, make_dropout(p, seed, tag),
+               out_row_needed, x_row_nonzero};
+    C2DSR_REQUIRE(!out_row_needed || (out != Y && out != Z), "a row mask needs out distinct from the addends");
+    if (out_row_needed) cudaMemsetAsync(out, 0, (size_t)n_rows * d * 4, (cudaStream_t)stream);   // unwanted rows = 0
     if (a.dr.p == 0.f) a.drop_mode = 0;
     constexpr int kRowsPerWarp = C2DSR_SPMM_RPW;
     const unsigned blocks = (unsigned)ceil_div(n_rows, 8 * kRowsPerWarp);

@@ -24,14 +24,25 @@ def _f(t: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # K2: GCN propagation (models/encoders.py:42-48)
 # ------------------------------------------------------------------------------------------------
-def spmm(csr, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_mode=0, p=0.0, seed=0, tag=0):
-    """csr = (rowptr, col, val, long_rows or None) as held by graph.CsrGraph (.fwd / .bwd)."""
+def mark_rows(ids, n_rows: int):
+    """uint8 [n_rows] with 1 at every id that occurs in ``ids`` (int64, any shape)."""
+    ids = ids.contiguous()
+    mask = torch.empty(n_rows, dtype=torch.uint8, device=ids.device)
+    call("c2dsr_mark_rows", ptr(ids, I64), ids.numel(), n_rows, ptr(mask), stream())
+    return mask
+
+
+def spmm(csr, X, Y=None, Z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, drop_mode=0, p=0.0, seed=0, tag=0,
+         out_need=None, x_nz=None):
+    """csr = (rowptr, col, val, long_rows or None) as held by graph.CsrGraph (.fwd / .bwd).  ``out_need`` /
+    ``x_nz``: optional uint8 row masks (see the header): rows not wanted are left zero, all-zero rows of X are
+    skipped."""
     rowptr, col, val, long_rows = csr
     n, d = X.shape
     out = torch.empty_like(X) if out is None else out
     call("c2dsr_spmm", ptr(rowptr, I32), ptr(col, I32), ptr(val, F32), ptr(long_rows),
          0 if long_rows is None else long_rows.numel(), ptr(X, F32), ptr(Y), ptr(Z), ptr(out, F32), n, d, alpha, beta,
-         gamma, drop_mode, p, seed, seed_tag(seed, tag), stream())
+         gamma, drop_mode, p, seed, seed_tag(seed, tag), ptr(out_need), ptr(x_nz), stream())
     return out
 
 
@@ -42,19 +53,7 @@ class GCNFn(torch.autograd.Function):
     def forward(ctx, E, graph, n_gnn: int, p: float, seed: int, tag: int):
         E = _f(E)
         ctx.graph, ctx.n_gnn, ctx.p, ctx.seed, ctx.tag = graph, n_gnn, p, seed, tag
-        if n_gnn == 0:
-            return E.clone()
-        c = 1.0 / (n_gnn + 1)
-        g = graph
-        h, acc = E, E
-        for j in range(1, n_gnn + 1):
-            t = tag * 16 + j
-            if j == n_gnn:
-                return spmm(g.fwd, h, Y=acc, alpha=c, beta=c, drop_mode=1, p=p, seed=seed, tag=t)
-            h = spmm(g.fwd, h, drop_mode=1, p=p, seed=seed, tag=t)
-            nxt = torch.empty_like(h)
-            call("c2dsr_axpby", ptr(h), ptr(acc), ptr(nxt), h.numel(), 1.0, 1.0, stream())
-            acc = nxt
+        return gcn_forward(E, graph, n_gnn, p, seed, tag)
 
     @staticmethod
     def backward(ctx, d_hi):
@@ -65,16 +64,35 @@ class GCNFn(torch.autograd.Function):
         return gcn_backward(g, d_hi, k, p, seed, tag), None, None, None, None, None
 
 
-def gcn_backward(g, d_hi, k: int, p: float, seed: int, tag: int, direct: bool = False, pad_idx: int = -1):
+def gcn_forward(E, g, n_gnn: int, p: float, seed: int, tag: int, need=None):
+    """hi = mean([E, A drop(E), A drop(A drop(E)), ...]) (models/encoders.py:42-48), n_gnn SpMMs.  ``need``
+    (uint8 row mask): only those rows of hi are wanted -- the last product skips the others (left zero)."""
+    if n_gnn == 0:
+        return E.clone()
+    c = 1.0 / (n_gnn + 1)
+    h, acc = E, E
+    for j in range(1, n_gnn + 1):
+        t = tag * 16 + j
+        if j == n_gnn:
+            return spmm(g.fwd, h, Y=acc, alpha=c, beta=c, drop_mode=1, p=p, seed=seed, tag=t, out_need=need)
+        h = spmm(g.fwd, h, drop_mode=1, p=p, seed=seed, tag=t)
+        nxt = torch.empty_like(h)
+        call("c2dsr_axpby", ptr(h), ptr(acc), ptr(nxt), h.numel(), 1.0, 1.0, stream())
+        acc = nxt
+
+
+def gcn_backward(g, d_hi, k: int, p: float, seed: int, tag: int, direct: bool = False, pad_idx: int = -1,
+                 nz=None):
     """Gradient w.r.t. E of hi = GCN(E) (k >= 1 hops) given d_hi:  g_k = c d_hi,  g_{j-1} = c d_hi + m_j .* (A^T g_j).
     ``direct=True`` folds in the gradient of the branch's direct look-up E[seq] as well, which equals d_hi on every
     row except the pad row (``nn.Embedding(padding_idx)`` blocks it there): the last product then uses
     beta = c + 1 and the pad row is corrected, so neither a second dense [N, d] gradient nor the add of the two
-    is ever materialised."""
+    is ever materialised.  ``nz`` (uint8 row mask): rows of d_hi outside it are exactly zero (items the batch
+    did not touch) and the first product skips them."""
     c = 1.0 / (k + 1)
     extra = 1.0 if direct else 0.0
     cur = spmm(g.bwd, d_hi, Y=d_hi, alpha=c, beta=c + (extra if k == 1 else 0.0), drop_mode=2, p=p, seed=seed,
-               tag=tag * 16 + k)
+               tag=tag * 16 + k, x_nz=nz)
     for j in range(k - 1, 0, -1):
         cur = spmm(g.bwd, cur, Y=d_hi, alpha=1.0, beta=c + (extra if j == 1 else 0.0), drop_mode=2, p=p, seed=seed,
                    tag=tag * 16 + j)
@@ -205,7 +223,9 @@ class BranchSetFn(torch.autograd.Function):
     norm_first, dense_passes, n_w, gcn); ``streams``: per branch a torch.cuda.Stream or None (= the caller's
     stream); ``flat``: per branch hi, E, P and the n_w encoder weights.  ``gcn`` = (graph, n_gnn, p, seed,
     tag) says that ``hi`` (passed detached) is GCN(E) of the same step: the backward then continues through
-    the propagation on the branch's own stream and returns the whole gradient of E (see gcn_backward)."""
+    the propagation on the branch's own stream and returns the whole gradient of E (see gcn_backward).  With
+    ``gcn`` given and ``hi`` = None the propagation itself is also computed here, on the branch's stream, and
+    returned as an extra (non-differentiable) output after the branch outputs."""
 
     @staticmethod
     def forward(ctx, specs, streams, *flat):
@@ -214,9 +234,10 @@ class BranchSetFn(torch.autograd.Function):
         parts = []
         for sp in specs:
             n = 3 + sp["n_w"]
-            parts.append([_f(t) for t in flat[off:off + n]])
+            parts.append([None if t is None else _f(t) for t in flat[off:off + n]])
             off += n
         order = sorted(range(len(specs)), key=lambda i: streams[i] is None)      # side streams first
+        his = [None] * len(specs)
         for i in order:
             sp, (hi, E, P, *w) = specs[i], parts[i]
             seq, pos = sp["seq"].contiguous(), sp["pos"].contiguous()
@@ -224,6 +245,9 @@ class BranchSetFn(torch.autograd.Function):
             if st is not cur:
                 st.wait_stream(cur)
             with torch.cuda.stream(st):
+                if hi is None:                       # propagate on this branch's stream, only the rows the batch reads
+                    graph, k, gp, gseed, gtag = sp["gcn"]
+                    hi = his[i] = gcn_forward(E, graph, k, gp, gseed, gtag, need=mark_rows(seq, E.shape[0]))
                 x = _gather_forward(hi, E, P, seq, pos, sp["scale"], sp["p"], sp["seed"], sp["gather_tag"])
                 out, saved = _encoder_forward(x, seq, w, sp["n_head"], sp["pad"], sp["norm_first"], sp["p"],
                                               sp["seed"], sp["encoder_tag"], sp["dense_passes"])
@@ -236,7 +260,9 @@ class BranchSetFn(torch.autograd.Function):
         ctx.specs, ctx.streams = specs, streams
         ctx.meta = [(i, seq, pos, hs, ps, os, nw) for i, _, seq, pos, hs, ps, os, nw in keep]
         ctx.save_for_backward(*[k[1] for k in keep], *[t for prt in parts for t in prt[3:]])
-        return tuple(outs)
+        extra = tuple(h for h in his if h is not None)
+        ctx.mark_non_differentiable(*extra)
+        return tuple(outs) + extra
 
     @staticmethod
     def backward(ctx, *d_outs):
@@ -268,7 +294,8 @@ class BranchSetFn(torch.autograd.Function):
                 del dx
                 if gcn is not None:
                     graph, k, gp, gseed, gtag = gcn
-                    d_E = gcn_backward(graph, d_hi, k, gp, gseed, gtag, direct=True, pad_idx=sp["pad"])
+                    d_E = gcn_backward(graph, d_hi, k, gp, gseed, gtag, direct=True, pad_idx=sp["pad"],
+                                       nz=mark_rows(seq, hi_shape[0]))
                     d_hi = None
             result[i] = [d_hi, d_E, d_P, *grads]
         for st in streams:

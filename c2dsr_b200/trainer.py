@@ -218,7 +218,7 @@ class Trainer(object):
         a fixed row capacity (rows beyond the batch's valid count are ignore_index rows, which contribute
         nothing); a batch with more valid rows than that, or any other shape, takes the eager path."""
         if not (self.use_graph and self.model.training):
-            self.model.convolve_graph()
+            self.model.convolve_graph(lazy=True)
             return self.train_batch(batch)
         nv = self._valid_rows(batch) if self.skip_ignored else None
         key = (tuple(batch[0].shape), nv is not None)
@@ -236,12 +236,13 @@ class Trainer(object):
                 g["overflows"] += 1
                 if g["overflows"] >= 8:                                  # the capacity was a bad guess: re-capture
                     del self._graphs[key]
-            self.model.convolve_graph()
+            self.model.convolve_graph(lazy=True)
             return self.train_batch(batch)
         for s, x in zip(g["static"], batch):
             s.copy_(x, non_blocking=True)
         self.optimizer.sync_lr()
         g["graph"].replay()
+        self.model.hi_share, self.model.hi_a, self.model.hi_b = g["hi"]      # Q13: the step's propagations stay cached
         _cabi.REPLAYED_LAUNCHES += g["launches"]
         self.optimizer.n_steps += 1
         out = g["out"].clone()
@@ -268,12 +269,13 @@ class Trainer(object):
         self._caps = caps
         try:
             with torch.cuda.graph(graph):
-                self.model.convolve_graph()
+                self.model.convolve_graph(lazy=True)
                 out = torch.stack(self.train_batch(static))
         finally:
             self._caps = None
         g = dict(graph=graph, static=static, out=out, caps=caps or (2 * B * R, 2 * B * R),
-                 launches=_cabi.launch_count() - l0, overflows=0)
+                 launches=_cabi.launch_count() - l0, overflows=0,
+                 hi=(self.model.hi_share, self.model.hi_a, self.model.hi_b))
         self._graphs[key] = g
         return g
 

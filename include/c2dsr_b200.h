@@ -58,10 +58,17 @@ int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, fl
  * drop_mode 2: out = alpha * m .* (A X) + ...      (mask indexed by the output row: backward, A = A^T)
  * Y, Z may be NULL; out may alias Y or Z (not X).  long_rows (optional, device) lists the rows that are
  * split across a CTA to bound the heavy tail.  replaces torch.spmm(adj, h) + stack/mean
- * (models/encoders.py:43-48) and its autograd transpose product. */
+ * (models/encoders.py:43-48) and its autograd transpose product.
+ * Optional byte masks (NULL = none), both exact:  out_row_needed [n_rows]: rows with 0 are not computed and
+ * are left zero (a training step only reads the rows of the items in its batch: hi[seq]);  x_row_nonzero
+ * [columns of A]: rows of X flagged 0 are known to be all zero and their entries are skipped (the gradient
+ * d_hi is non-zero only on the rows the batch touched).  c2dsr_mark_rows builds such a mask from item ids. */
 int c2dsr_spmm(const int32_t* rowptr, const int32_t* col, const float* val, const int32_t* long_rows, int n_long,
                const float* X, const float* Y, const float* Z, float* out, int64_t n_rows, int d, float alpha,
-               float beta, float gamma, int drop_mode, float p, uint64_t seed, uint64_t tag, void* stream);
+               float beta, float gamma, int drop_mode, float p, uint64_t seed, uint64_t tag,
+               const uint8_t* out_row_needed, const uint8_t* x_row_nonzero, void* stream);
+/* mask[k] = 1 for every k in ids[0..n) (0 <= k < n_rows), 0 elsewhere */
+int c2dsr_mark_rows(const int64_t* ids, int64_t n, int64_t n_rows, uint8_t* mask, void* stream);
 /* Rows with more non-zeros than this should be listed in long_rows (they get a whole CTA each). */
 int c2dsr_spmm_long_row_threshold(void);
 

@@ -41,6 +41,17 @@ for e in ev:
     by_stream.setdefault(getattr(e, "device_resource_id", getattr(e, "device_index", 0)), [0, 0.0])
     by_stream[getattr(e, "device_resource_id", getattr(e, "device_index", 0))][0] += 1
     by_stream[getattr(e, "device_resource_id", getattr(e, "device_index", 0))][1] += e.device_time
+# ordered kernel sequence of the last step on the main stream
+main = max(by_stream, key=lambda k: by_stream[k][1])
+evs = sorted([e for e in ev if getattr(e, "device_resource_id", 0) == main], key=lambda e: e.time_range.start)
+evs = evs[-(len(evs) // N):]
+prev = None
+print("---- main-stream sequence (start us rel, dur us, gap us, name)")
+t00 = evs[0].time_range.start
+for e in evs:
+    gap = (e.time_range.start - prev) if prev is not None else 0
+    print(f"{e.time_range.start - t00:8.1f} {e.device_time:7.1f} {gap:6.1f}  {e.name[:70]}")
+    prev = e.time_range.end
 print("per-stream busy us/step:", {k: (v[0] / N, round(v[1] / N, 1)) for k, v in by_stream.items()})
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k}")

@@ -116,6 +116,32 @@ def test_spmm_vs_sparse_mm(d):
     assert rel_err(Yd.cpu(), torch.sparse.mm(A, X) + Y) < 2e-6
 
 
+@pytest.mark.parametrize("d,p", [(64, 0.0), (256, 0.25)])
+def test_spmm_row_masks_are_exact(d, p):
+    """out_row_needed: wanted rows bit-identical to the unmasked product, the others zero; x_row_nonzero:
+    skipping rows of X that are all zero changes nothing (what a training step relies on: only the rows of the
+    batch's items are propagated forward, only the rows it touched carry gradient backward)."""
+    ops, _ = _ops()
+    from c2dsr_b200.graph import CsrGraph
+    g = torch.Generator().manual_seed(d)
+    n = 3001
+    A = _random_csr(n, d, g, heavy=300)
+    G = CsrGraph(A, DEV)
+    X, Y = torch.randn(n, d, generator=g).to(DEV), torch.randn(n, d, generator=g).to(DEV)
+    ids = torch.randint(0, n, (400,), generator=g).to(DEV)
+    need = ops.mark_rows(ids, n)
+    assert int(need.sum()) == int(torch.unique(ids).numel())
+    kw = dict(alpha=0.5, beta=0.5, drop_mode=1, p=p, seed=5, tag=9)
+    full = ops.spmm(G.fwd, X, Y=Y, **kw)
+    part = ops.spmm(G.fwd, X, Y=Y, out_need=need, **kw)
+    sel = need.bool()
+    assert torch.equal(part[sel], full[sel]) and float(part[~sel].abs().max()) == 0.0
+    Xz = X.clone()
+    Xz[~sel] = 0.0                                              # rows outside the mask are exactly zero
+    kw2 = dict(alpha=0.5, beta=1.5, drop_mode=2, p=p, seed=5, tag=10)
+    assert torch.equal(ops.spmm(G.bwd, Xz, Y=Xz, x_nz=need, **kw2), ops.spmm(G.bwd, Xz, Y=Xz, **kw2))
+
+
 @pytest.mark.parametrize("n_gnn,p", [(1, 0.0), (2, 0.0), (3, 0.0), (1, 0.3), (2, 0.3)])
 def test_gcn_forward_backward(n_gnn, p):
     """GCN mean-of-hops vs the oracle; with dropout the check is the adjoint identity
