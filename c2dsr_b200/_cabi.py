@@ -78,6 +78,10 @@ _PROTOS = {
     "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp]),
     "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp]),
     "c2dsr_adamw_amsgrad": (i32, [vp, i32, i64, f32, f32, f32, f32, f32, i32, vp]),
+    "c2dsr_loss_rows_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                  vp]),
+    "c2dsr_loss_rows_bwd_workspace_bytes": (i64, [i64, i32]),
+    "c2dsr_loss_rows_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, vp, vp, vp, vp, vp, i64, vp]),
     "c2dsr_graph_build_workspace_bytes": (i64, [i64, i64]),
     "c2dsr_graph_build": (i32, [vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, i64, vp]),
     "c2dsr_step_state_bytes": (i32, []),

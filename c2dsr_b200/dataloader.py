@@ -200,6 +200,11 @@ class CDSRDataset(torch.utils.data.Dataset):
             self.fields = [x.pin_memory() for x in self.fields]
         else:
             self.fields = [x.to(device) for x in self.fields]
+            if self.mode == "train" and len({(tuple(x.shape), x.dtype) for x in self.fields}) == 1 \
+                    and self.fields[0].is_cuda:
+                # one [n_fields, n, L] block; the fields become views of it, a batch is ONE slice / gather
+                self.stacked = torch.stack(self.fields, 0)
+                self.fields = list(self.stacked.unbind(0))
         return self
 
     def __len__(self):
@@ -210,8 +215,10 @@ class CDSRDataset(torch.utils.data.Dataset):
 
 
 class Batch(tuple):
-    """A batch tuple that can carry host-side facts about itself (``n_valid``: rows of the A / B loss GEMMs)."""
+    """A batch tuple that can carry host-side facts about itself (``n_valid``: rows of the A / B loss GEMMs) and,
+    for a device-resident training split, the one ``[14, B, L]`` tensor its fields are views of (``packed``)."""
     n_valid = None
+    packed = None
 
 
 class BatchLoader:
@@ -254,12 +261,24 @@ class BatchLoader:
             if self.world_size > 1:                     # data-parallel: contiguous slice of the global batch
                 per = (hi - lo + self.world_size - 1) // self.world_size
                 lo, hi = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
+            stacked = getattr(self.dataset, "stacked", None)
             if order is None:
-                out = Batch(x[lo:hi] for x in self.dataset.fields)
+                if stacked is not None:
+                    packed = stacked[:, lo:hi]
+                    out = Batch(packed.unbind(0))
+                    out.packed = packed
+                else:
+                    out = Batch(x[lo:hi] for x in self.dataset.fields)
                 if counts is not None:
                     out.n_valid = (tuple(int(v) for v in counts[lo:hi].sum(0)), na, nb)
             else:
-                out = Batch(x.index_select(0, order[lo:hi].to(dev)) for x in self.dataset.fields)
+                idx = order[lo:hi].to(dev)
+                if stacked is not None:
+                    packed = stacked.index_select(1, idx)
+                    out = Batch(packed.unbind(0))
+                    out.packed = packed
+                else:
+                    out = Batch(x.index_select(0, idx) for x in self.dataset.fields)
                 if counts is not None:
                     out.n_valid = (tuple(int(v) for v in counts.index_select(0, order[lo:hi]).sum(0)), na, nb)
             yield out

@@ -462,6 +462,67 @@ class ScoreCETcFn(torch.autograd.Function):
         return dH, dHpad, dW, db, dwpad, dbpad, None, None, None
 
 
+class DomainLossTcFn(torch.autograd.Function):
+    """The recommendation loss of one domain (trainer.py:122-152) from the encoder outputs themselves:
+    h_share, h_dom [B, L, d], targets gt_share, gt_dom [B, L] (ignore = n_cls), the last R positions.  Row
+    assembly (c2dsr_loss_rows_*) + the tcgen05 logits / cross-entropy (c2dsr_score_ce_*_tc) in one autograd node;
+    M = number of rows sent through the GEMMs (valid rows first; 2 B R = all, like the reference)."""
+
+    @staticmethod
+    def forward(ctx, h_share, h_dom, W, b, wpad, bpad, gt_share, gt_dom, w_share, n_dom, R: int, M: int, passes: int):
+        h_share, h_dom, W, b, wpad, bpad = (_f(t) for t in (h_share, h_dom, W, b, wpad, bpad))
+        gt_share, gt_dom = gt_share.contiguous(), gt_dom.contiguous()
+        w_share, n_dom = _f(w_share).reshape(1), _f(n_dom).reshape(1)
+        B, L, d = h_share.shape
+        N = W.shape[0]
+        dev = h_share.device
+        perm = torch.empty(2 * B * R, device=dev, dtype=I64)
+        inv = torch.empty(2 * B * R, device=dev, dtype=I32)
+        H = torch.empty(M, d, device=dev, dtype=F32)
+        gt = torch.empty(M, device=dev, dtype=I64)
+        w = torch.empty(M, device=dev, dtype=F32)
+        zpad = torch.empty(M, device=dev, dtype=F32)
+        call("c2dsr_loss_rows_fwd", ptr(h_share), ptr(h_dom), ptr(gt_share, I64), ptr(gt_dom, I64), B, L, R, d, N, M,
+             ptr(w_share), ptr(n_dom), ptr(wpad), ptr(bpad), ptr(perm), ptr(inv), ptr(H), ptr(gt), ptr(w), ptr(zpad),
+             stream())
+        loss = torch.zeros((), device=dev, dtype=F32)
+        lse = torch.empty(M, device=dev, dtype=F32)
+        if M > 0:
+            loss_row = torch.empty(M, device=dev, dtype=F32)
+            ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 0), dev)
+            call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, passes, ptr(lse),
+                 ptr(loss_row), ptr(ws), ws.numel(), stream())
+            call("c2dsr_wsum", ptr(loss_row), ptr(w), M, ptr(loss), stream())
+        ctx.save_for_backward(h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse)
+        ctx.cfg = (R, M, passes)
+        return loss
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse = ctx.saved_tensors
+        R, M, passes = ctx.cfg
+        B, L, d = h_share.shape
+        N = W.shape[0]
+        dev = h_share.device
+        dH = torch.empty(M, d, device=dev, dtype=F32)
+        dW = torch.zeros(N, d, device=dev, dtype=F32)
+        db = torch.zeros(N, device=dev, dtype=F32)
+        dzpad = torch.empty(M, device=dev, dtype=F32)
+        if M > 0:
+            coef = (w * d_loss).contiguous()
+            ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 1), dev)
+            call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d,
+                 passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
+        d_share = torch.empty_like(h_share)
+        d_dom = torch.empty_like(h_dom)
+        dwpad = torch.empty(1, d, device=dev, dtype=F32)
+        dbpad = torch.empty(1, device=dev, dtype=F32)
+        ws = workspace.get(query("c2dsr_loss_rows_bwd_workspace_bytes", M, d), dev)
+        call("c2dsr_loss_rows_bwd", ptr(dH), ptr(dzpad), ptr(h_share), ptr(h_dom), ptr(wpad), ptr(perm), ptr(inv), B, L,
+             R, d, M, ptr(d_share), ptr(d_dom), ptr(dwpad), ptr(dbpad), ptr(ws), ws.numel(), stream())
+        return d_share, d_dom, dW, db, dwpad, dbpad, None, None, None, None, None, None, None
+
+
 def compact_rows(gt: torch.Tensor, ignore: int) -> torch.Tensor:
     """Stable partition of the row indices: rows with gt != ignore first (int64 [M])."""
     gt = gt.contiguous()

@@ -156,6 +156,20 @@ class Trainer(object):
         loss_mi = ops.InfomaxFn.apply(h_share, hx, hy, h_neg_a, h_neg_b, m.D_a.weight, m.D_b.weight, m.D_a.bias,
                                       m.D_b.bias, gt_mask_a, gt_mask_b, 1.0 / (B * self.world_size))
 
+        if self.score_path == "tc":
+            # row assembly + tcgen05 logits / cross-entropy as one node per domain (ops.DomainLossTcFn)
+            w_share = 1.0 / (R * b_glob)
+            parts = []
+            for k, (h_dom, cls, g_share, g_dom, n_dom) in enumerate(((hx, m.classifier_a, gt_share_a, gt_a, n_a),
+                                                                     (hy, m.classifier_b, gt_share_b, gt_b, n_b))):
+                rows = 2 * B * R if n_valid is None else min(int(n_valid[k]), 2 * B * R)
+                parts.append(ops.DomainLossTcFn.apply(h_share, h_dom, cls.weight, cls.bias, m.classifier_pad.weight,
+                                                      m.classifier_pad.bias, g_share, g_dom, w_share, n_dom, R, rows,
+                                                      self.tc_passes))
+            loss_rec = parts[0] + parts[1]
+            loss = self.lambda_loss * loss_rec + (1 - self.lambda_loss) * loss_mi
+            return loss, loss_rec, loss_mi
+
         hs = h_share[:, -R:].reshape(-1, d)
         ha, hb = hx[:, -R:].reshape(-1, d), hy[:, -R:].reshape(-1, d)
         share_w = (1.0 / (R * b_glob)).expand(B * R)
@@ -238,8 +252,12 @@ class Trainer(object):
                     del self._graphs[key]
             self.model.convolve_graph(lazy=True)
             return self.train_batch(batch)
-        for s, x in zip(g["static"], batch):
-            s.copy_(x, non_blocking=True)
+        packed = getattr(batch, "packed", None)
+        if packed is not None and packed.shape == g["packed"].shape:
+            g["packed"].copy_(packed, non_blocking=True)                 # one copy for the 14 fields
+        else:
+            for s, x in zip(g["static"], batch):
+                s.copy_(x, non_blocking=True)
         self.optimizer.sync_lr()
         g["graph"].replay()
         self.model.hi_share, self.model.hi_a, self.model.hi_b = g["hi"]      # Q13: the step's propagations stay cached
@@ -254,7 +272,12 @@ class Trainer(object):
         if key[1]:
             top = [max(x[k] for x in seen) for k in (0, 1)]
             caps = tuple(min(2 * B * R, -(-int(1.08 * t + 32) // 128) * 128) for t in top)
-        static = tuple(torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in batch)
+        if len({(tuple(x.shape), x.dtype) for x in batch}) == 1:
+            packed_static = torch.empty((len(batch),) + tuple(batch[0].shape), dtype=batch[0].dtype, device=self.device)
+            static = tuple(packed_static.unbind(0))
+        else:
+            packed_static = None
+            static = tuple(torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in batch)
         for s, x in zip(static, batch):
             s.copy_(x)
         self.optimizer.sync_lr()
@@ -275,6 +298,7 @@ class Trainer(object):
             self._caps = None
         g = dict(graph=graph, static=static, out=out, caps=caps or (2 * B * R, 2 * B * R),
                  launches=_cabi.launch_count() - l0, overflows=0,
+                 packed=packed_static if packed_static is not None else torch.empty(0),
                  hi=(self.model.hi_share, self.model.hi_a, self.model.hi_b))
         self._graphs[key] = g
         return g

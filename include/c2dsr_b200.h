@@ -238,6 +238,24 @@ typedef struct {
 int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, float lr, float beta1,
                         float beta2, float eps, float weight_decay, int step, void* stream);
 
+/* ---- K4a row assembly (trainer.py:122-152: slices of the last len_rec positions, cat, add, ignore rows) ----
+ * The 2 B R virtual loss rows of one domain -- B R "share" rows (H = Hpad = h_share[b, l], target gt_share) then
+ * B R "domain" rows (H = h_share + h_dom, Hpad = h_dom, target gt_dom), (b, l) over the last R positions -- are
+ * stably partitioned (rows whose target != ignore first) and the first M are emitted: H [M, d], gt [M],
+ * w [M] (*w_share for share rows, 1 / *n_dom for domain rows; device scalars) and the pad logit
+ * zpad [M] = Hpad . wpad + bpad.  perm [2BR] / inv [2BR] (inv[perm[r]] = r) are kept for the backward, which
+ * writes d h_share and d h_dom for EVERY token ([B, L, d], zeros outside the last R positions) from dH [M, d]
+ * and dzpad [M] (d Hpad = dzpad wpad^T is never materialised) and d wpad [d], d bpad [1]. */
+int c2dsr_loss_rows_fwd(const float* h_share, const float* h_dom, const int64_t* gt_share, const int64_t* gt_dom,
+                        int64_t B, int L, int R, int d, int64_t ignore, int64_t M, const float* w_share,
+                        const float* n_dom, const float* wpad, const float* bpad, int64_t* perm, int32_t* inv, float* H,
+                        int64_t* gt, float* w, float* zpad, void* stream);
+int64_t c2dsr_loss_rows_bwd_workspace_bytes(int64_t M, int d);
+int c2dsr_loss_rows_bwd(const float* dH, const float* dzpad, const float* h_share, const float* h_dom, const float* wpad,
+                        const int64_t* perm, const int32_t* inv, int64_t B, int L, int R, int d, int64_t M,
+                        float* d_h_share, float* d_h_dom, float* dwpad, float* dbpad, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* ---- adjacency builder (utils/graph.py:33-96: preprocess_graph + normalize) -------------------
  * Raw directed transitions (src[i] -> dst[i], duplicates allowed) to the CSR of A = D^-1 (summed counts)
  * (transpose = 0) or of A^T (transpose = 1; values still divided by the row sum of the SOURCE item).
