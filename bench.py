@@ -387,6 +387,7 @@ def run_b200(a):
         # stuck communicator teardown turn a finished measurement into a hang
         import gc
         tr._graphs.clear()
+        tr._eval_graph = None
         gc.collect()
         torch.cuda.synchronize()
         t = threading.Thread(target=torch.distributed.destroy_process_group, daemon=True)
