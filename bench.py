@@ -354,7 +354,10 @@ def run_b200(a):
                      "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tensor"], "unit": "TFLOP/s",
                      "frac": round(ach / pk["tensor"], 5),
                      # DRAM bytes of the K4a launches of one step, ncu --set full (profiles/r01_ncu_full_kernels.md)
-                     "traffic": 5.8e9 if (a.score_path == "tc" and a.workload == "fk" and a.tc_passes == 3 and a.all_rows) else None,
+                     # (profiles/r01_step_kernels_4p0ms.md: log-sum-exp, dZ-emitting, two gradient GEMMs, dZ column sums,
+                     #  slab reductions, bf16 splits; rows with a target only)
+                     "traffic": 3.29e9 if (a.score_path == "tc" and a.workload == "fk" and a.tc_passes == 3
+                                           and not a.all_rows) else None,
                      "peak_source": pk["src"] + " sustained",
                      "algorithmic_gflop_per_step": round(flops_step / 1e9, 1),
                      "rows_with_target_frac": round(rows_frac, 4),

@@ -116,7 +116,7 @@ __global__ void loss_rows_bwd_kernel(const float* __restrict__ dH, const float* 
 }
 
 // d w_pad = sum_r dzpad[r] * Hpad[r], d b_pad = sum_r dzpad[r]: chunk partials (fixed order), then a final sum
-constexpr int kPadChunk = 64;
+constexpr int kPadChunk = 16;     // short serial chains (each row costs a dependent perm -> row load)
 __global__ void loss_rows_wpad_partial_kernel(const float* __restrict__ h_share, const float* __restrict__ h_dom,
                                               const float* __restrict__ dzpad, const int64_t* __restrict__ perm, RowGeom g,
                                               int64_t M, float* __restrict__ partial) {
