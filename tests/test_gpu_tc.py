@@ -123,3 +123,49 @@ def test_gemm_tc_all_layouts(ta, tb, M, N, K):
     ops.gemm_tc(ta, tb, M, N, K, A.to(DEV), A.shape[1], B.to(DEV), B.shape[1], Cd, N, beta=1.0, bias=bias.to(DEV), act=1)
     err = float((Cd.cpu().double() - ref).abs().max()) / float(ref.abs().max())
     assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("frac", [1.0, 0.55, 0.0])
+def test_domain_loss_rows_vs_torch(frac):
+    """ops.DomainLossTcFn (row partition + emit, tcgen05 logits / CE, backward through the inverse permutation)
+    against plain torch on the same tensors (trainer.py:122-152 written out): loss and all gradients.  ``frac`` of
+    the valid rows go through the GEMMs: 1.0 = exactly the rows that carry a target, 0.55 = fewer (the dropped rows
+    then contribute nothing, as documented for M), 0.0 = none."""
+    from c2dsr_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, L, R, d, N = 24, 15, 10, 64, 777
+    hs = torch.randn(B, L, d, generator=g).to(DEV).requires_grad_(True)
+    hd = torch.randn(B, L, d, generator=g).to(DEV).requires_grad_(True)
+    W = (0.1 * torch.randn(N, d, generator=g)).to(DEV).requires_grad_(True)
+    b = (0.1 * torch.randn(N, generator=g)).to(DEV).requires_grad_(True)
+    wpad = (0.1 * torch.randn(1, d, generator=g)).to(DEV).requires_grad_(True)
+    bpad = torch.randn(1, generator=g).to(DEV).requires_grad_(True)
+
+    def targets():
+        t = torch.randint(0, N, (B, L), generator=g)
+        t[torch.rand(B, L, generator=g) < 0.6] = N                     # ignore class
+        return t.to(DEV)
+    gs, gd = targets(), targets()
+    valid = int((gs[:, -R:] != N).sum() + (gd[:, -R:] != N).sum())
+    n_dom = (gd[:, -R:] != N).sum().float()
+    w_share = torch.tensor(1.0 / (R * B), device=DEV)
+    M = int(round(frac * valid))
+    loss = ops.DomainLossTcFn.apply(hs, hd, W, b, wpad, bpad, gs, gd, w_share, n_dom, R, M, 3)
+    loss.backward()
+    got = [loss.detach()] + [t.grad.clone() for t in (hs, hd, W, b, wpad, bpad)]
+    for t in (hs, hd, W, b, wpad, bpad):
+        t.grad = None
+    # torch restatement: virtual rows in the same order, first M valid ones kept
+    hsr, hdr = hs[:, -R:].reshape(-1, d), hd[:, -R:].reshape(-1, d)
+    H = torch.cat((hsr, hsr + hdr))
+    Hp = torch.cat((hsr, hdr))
+    gt = torch.cat((gs[:, -R:].reshape(-1), gd[:, -R:].reshape(-1)))
+    w = torch.cat((w_share.expand(B * R), (1.0 / n_dom).expand(B * R)))
+    keep = torch.nonzero(gt != N).view(-1)[:M]
+    Z = torch.cat((H[keep] @ W.t() + b, Hp[keep] @ wpad.t() + bpad), 1)
+    ref = (torch.nn.functional.cross_entropy(Z, gt[keep], reduction="none") * w[keep]).sum() if M else Z.sum() * 0
+    ref.backward()
+    want = [ref.detach()] + [t.grad if t.grad is not None else torch.zeros_like(t) for t in (hs, hd, W, b, wpad, bpad)]
+    for a, c, nm in zip(got, want, ("loss", "d_h_share", "d_h_dom", "dW", "db", "dwpad", "dbpad")):
+        scale = float(c.abs().max()) + 1e-12
+        assert float((a - c).abs().max()) <= 2e-4 * scale + 1e-7, (nm, float((a - c).abs().max()), scale)
