@@ -99,3 +99,61 @@ class GradBucket:
             o += n
         allreduce_sum_(self.flat)
         return views
+
+
+class FlatShards:
+    """Sharded optimiser step for data-parallel training (ZeRO-1 style; same bytes on the wire as one
+    all-reduce, but every rank runs AdamW on 1/world of the parameters instead of all of them -- the update is
+    HBM-bound, 0.56 ms for the 67 M parameters of the Food-Kitchen shape).
+
+    The live parameters are re-pointed to views of ONE flat fp32 buffer (16-byte aligned offsets), which is cut
+    into ``world`` equal contiguous shards.  Per step: gradients are copied into a flat bucket,
+    reduce-scattered (sum) so that rank r holds the summed gradient of shard r, the optimiser updates
+    ``flat[shard r]`` in place, and an in-place all-gather refreshes the other shards of ``flat`` -- i.e. of every
+    parameter tensor -- on every rank.  Padding between tensors stays zero (AdamW maps 0 to 0)."""
+
+    ALIGN = 4            # floats
+
+    def __init__(self, params, rank: int, world_size: int):
+        self.params = list(params)
+        self.rank, self.world_size = rank, world_size
+        dev = self.params[0].device
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        per = (o + world_size - 1) // world_size
+        self.shard = (per + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        n = self.shard * world_size
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.bucket = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.grad_shard = torch.zeros(self.shard, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, off in zip(self.params, self.offsets):
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+        self.views = [self.bucket[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+
+    @property
+    def param_shard(self) -> torch.Tensor:
+        return self.flat[self.rank * self.shard:(self.rank + 1) * self.shard]
+
+    def reduce_scatter_grads(self) -> torch.Tensor:
+        """bucket <- this step's gradients; grad_shard <- sum over ranks of bucket[shard of this rank]."""
+        torch._foreach_copy_(self.views, [p.grad for p in self.params])
+        if dist.get_backend() == "gloo":                     # CPU tests: gloo has no reduce-scatter
+            dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM)
+            self.grad_shard.copy_(self.bucket[self.rank * self.shard:(self.rank + 1) * self.shard])
+        else:
+            dist.reduce_scatter_tensor(self.grad_shard, self.bucket, op=dist.ReduceOp.SUM)
+        return self.grad_shard
+
+    def all_gather_params(self):
+        """Every rank's updated shard -> the whole flat buffer (in place) on every rank."""
+        if dist.get_backend() == "gloo":
+            parts = [torch.empty_like(self.param_shard) for _ in range(self.world_size)]
+            dist.all_gather(parts, self.param_shard.clone())
+            self.flat.copy_(torch.cat(parts))
+        else:
+            dist.all_gather_into_tensor(self.flat, self.param_shard)

@@ -55,6 +55,32 @@ class FusedAdamW(torch.optim.Optimizer):
             call("c2dsr_step_state_set_lr", ptr(self.dyn_state), lr, stream())
             self._dyn_lr = lr
 
+    # ---- sharded data-parallel step: one contiguous fp32 range of a flat parameter buffer (dist.FlatShards) ----
+    @torch.no_grad()
+    def step_flat(self, p_shard: torch.Tensor, g_shard: torch.Tensor):
+        """AdamW-amsgrad on ``p_shard`` (in place) from the summed gradient ``g_shard`` of the same range; moments
+        and the per-epoch gradient sum are kept for this range only.  Needs the device step state."""
+        if self.dyn_state is None:
+            raise RuntimeError("step_flat needs attach_step_state()")
+        st = self.__dict__.get("_flat")
+        if st is None or st["p"] != p_shard.data_ptr() or st["g"] != g_shard.data_ptr():
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("the flat optimiser state must exist before a step is captured")
+            z = lambda: torch.zeros_like(p_shard)
+            st = self._flat = dict(p=p_shard.data_ptr(), g=g_shard.data_ptr(), m=z(), v=z(), vmax=z(), gsum=z())
+            host = (AdamTensor * 1)()
+            host[0].p, host[0].g, host[0].acc = ptr(p_shard), ptr(g_shard), ptr(st["gsum"])
+            host[0].m, host[0].v, host[0].vmax = ptr(st["m"]), ptr(st["v"]), ptr(st["vmax"])
+            host[0].n = p_shard.numel()
+            st["table"] = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(p_shard.device)
+        self.n_steps += 1
+        group = self.param_groups[0]
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        b1, b2 = group["betas"]
+        call("c2dsr_adamw_amsgrad_dyn", ptr(st["table"]), 1, p_shard.numel(), ptr(self.dyn_state), b1, b2, group["eps"],
+             group["weight_decay"], stream())
+
     def accumulated_grad(self, p):
         """The gradient sum since the last zero_grad() (= ``p.grad`` of the reference); None if p never had one."""
         if not self.accumulate:
@@ -67,6 +93,8 @@ class FusedAdamW(torch.optim.Optimizer):
             sums = [st["grad_sum"] for st in self.state.values() if "grad_sum" in st]
             if sums:
                 torch._foreach_zero_(sums)
+        if self.__dict__.get("_flat") is not None:
+            self._flat["gsum"].zero_()
 
     @torch.no_grad()
     def step(self, closure=None, grads: Optional[Dict[torch.nn.Parameter, torch.Tensor]] = None):

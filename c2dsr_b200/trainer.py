@@ -74,6 +74,7 @@ class Trainer(object):
         self.skip_ignored = bool(getattr(args, "skip_ignored_rows", True))
         self._wsplit = {}
         self.bucket = cdist.GradBucket()
+        self.shards = None           # data-parallel: flat parameter buffer + sharded optimiser step (lazy)
         # per-step device state: optimiser step number, learning rate and dropout key words (header:
         # c2dsr_step_state).  Eager and replayed steps read the same state, so they compute the same thing.
         self.step_state = torch.zeros(query("c2dsr_step_state_bytes"), dtype=torch.uint8, device=self.device)
@@ -217,7 +218,16 @@ class Trainer(object):
         loss, loss_rec, loss_mi = self.losses(batch)
         loss.backward()
         if self.world_size > 1:
-            self.optimizer.step(grads=self.bucket.reduce(self.optimizer.param_groups[0]["params"]))
+            # sharded step: reduce-scatter the gradients, update this rank's 1/world of the flat parameter
+            # buffer, all-gather the parameters (dist.FlatShards)
+            if self.shards is None:
+                live = [p for p in self.optimizer.param_groups[0]["params"] if p.grad is not None]
+                self.shards = cdist.FlatShards(live, self.rank, self.world_size)
+            self.optimizer.step_flat(self.shards.param_shard, self.shards.reduce_scatter_grads())
+            self.shards.all_gather_params()
+            for p in self.shards.params:
+                p.grad = None
+            call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
             out = torch.stack((loss.detach(), loss_rec.detach(), loss_mi.detach()))
             cdist.allreduce_sum_(out)
             return out[0], out[1], out[2]

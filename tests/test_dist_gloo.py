@@ -36,6 +36,26 @@ def _worker(rank, world, port, ret):
     r0, r1 = cdist.shard_bounds(37, rank, world)
     ok &= bool(torch.equal(cdist.allgather_rows(full[r0:r1].clone(), 37), full))
 
+    # --- sharded optimiser step plumbing (FlatShards): parameters become views of one flat buffer, gradients are
+    #     reduce-scattered, each rank updates its shard, the all-gather refreshes every parameter everywhere ---
+    torch.manual_seed(7)
+    ps = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)), torch.nn.Parameter(torch.randn(2, 2))]
+    before = [p.detach().clone() for p in ps]
+    sh = cdist.FlatShards(ps, rank, world)
+    ok &= all(torch.equal(p.detach(), b) for p, b in zip(ps, before))            # values survive the re-pointing
+    ok &= all(p.data_ptr() == sh.flat.data_ptr() + 4 * off for p, off in zip(ps, sh.offsets))
+    for i, p in enumerate(ps):
+        p.grad = torch.full_like(p, float((rank + 1) * (i + 1)))
+    g = sh.reduce_scatter_grads()
+    tot = sum(r + 1 for r in range(world))
+    expect = torch.zeros(sh.shard * world)
+    for i, (p, off) in enumerate(zip(ps, sh.offsets)):
+        expect[off:off + p.numel()] = tot * (i + 1)
+    ok &= bool(torch.equal(g, expect[rank * sh.shard:(rank + 1) * sh.shard]))
+    sh.param_shard.sub_(0.5 * g)                                                   # "optimiser": plain SGD on the shard
+    sh.all_gather_params()
+    ok &= all(torch.allclose(p.detach(), b - 0.5 * tot * (i + 1)) for i, (p, b) in enumerate(zip(ps, before)))
+
     # --- catalogue-sharded ranking: identical on every rank, equal to the unsharded oracle ---
     rng = np.random.default_rng(0)
     n_q, N, d = 37, 1003, 16
