@@ -442,6 +442,53 @@ def test_adamw_amsgrad_vs_oracle():
     assert torch.equal(dead.detach().cpu(), torch.ones(3))
 
 
+def test_adamw_device_step_state_and_gradient_sums():
+    """The modes the Trainer uses: optimiser-owned per-epoch gradient sum (accumulate=True), step number and
+    learning rate read from the device step state, and the flat sharded form (step_flat) -- all against the
+    oracle's AdamW-amsgrad on accumulated gradients; a learning-rate change reaches the device."""
+    from c2dsr_b200.optim import FusedAdamW
+    from c2dsr_b200._cabi import call, ptr, query, stream
+    g = torch.Generator().manual_seed(9)
+    shapes = [(200, 32), (32,), (7,)]
+    ps = [torch.randn(*s, generator=g) for s in shapes]
+    params = {str(i): p.clone() for i, p in enumerate(ps)}
+    opt_ref = oracle.AdamWAmsgrad(params, lr=1e-2, weight_decay=5e-4)
+    dev_p = [torch.nn.Parameter(p.to(DEV)) for p in ps]
+    opt = FusedAdamW(dev_p, lr=1e-2, weight_decay=5e-4, amsgrad=True, accumulate=True)
+    state = torch.zeros(query("c2dsr_step_state_bytes"), dtype=torch.uint8, device=DEV)
+    opt.attach_step_state(state)
+    call("c2dsr_step_begin", ptr(state), 123, stream())
+    # flat twin: the same parameters as one contiguous range
+    flat = torch.cat([p.reshape(-1) for p in ps]).to(DEV)
+    gflat = torch.empty_like(flat)
+    opt2 = FusedAdamW([torch.nn.Parameter(flat.clone())], lr=1e-2, weight_decay=5e-4, amsgrad=True)
+    state2 = torch.zeros_like(state)
+    opt2.attach_step_state(state2)
+    call("c2dsr_step_begin", ptr(state2), 123, stream())
+    for step in range(5):
+        if step == 3:                                              # scheduler-style change
+            for o in (opt, opt2):
+                o.param_groups[0]["lr"] = 5e-3
+            opt_ref.lr = 5e-3
+        grads = [torch.randn(*s, generator=g) * (10.0 ** -step) for s in shapes]
+        opt_ref.add_grads({str(i): gr for i, gr in enumerate(grads)})
+        opt_ref.step()
+        for p, gr in zip(dev_p, grads):
+            assert p.grad is None                                  # released by the previous step
+            p.grad = gr.to(DEV)
+        opt.step()
+        call("c2dsr_step_begin", ptr(state), 123, stream())
+        gflat.copy_(torch.cat([gr.reshape(-1) for gr in grads]).to(DEV))
+        opt2.step_flat(flat, gflat)
+        call("c2dsr_step_begin", ptr(state2), 123, stream())
+    for i, p in enumerate(dev_p):
+        assert rel_err(p.detach().cpu(), params[str(i)]) < 2e-6
+        assert rel_err(opt.accumulated_grad(p).cpu(), opt_ref.acc[str(i)]) < 1e-6
+    ref_flat = torch.cat([params[str(i)].reshape(-1) for i in range(len(ps))])
+    assert rel_err(flat.cpu(), ref_flat) < 2e-6
+    assert torch.equal(state.cpu()[:8], state2.cpu()[:8])          # both counted 6 steps
+
+
 # ------------------------------------------------------------------------------------------------
 # adjacency builder on the device vs the host path (utils/graph.py semantics)
 # ------------------------------------------------------------------------------------------------
