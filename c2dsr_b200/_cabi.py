@@ -68,8 +68,8 @@ _PROTOS = {
     "c2dsr_score_ce_bwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "c2dsr_compact_rows": (i32, [vp, i64, i64, vp, vp]),
     "c2dsr_score_ce_tc_workspace_bytes": (i64, [i64, i64, i32, i32]),
-    "c2dsr_score_ce_fwd_tc": (i32, [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, i64, vp]),
-    "c2dsr_score_ce_bwd_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
+    "c2dsr_score_ce_fwd_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, i64, vp]),
+    "c2dsr_score_ce_bwd_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "c2dsr_score_shard": (i32, [vp, vp, vp, i64, i64, i32, vp, i64, vp, i64, vp]),
     "c2dsr_pick_target": (i32, [vp, i64, vp, i64, i64, i64, vp, vp]),
     "c2dsr_rank_from_scores": (i32, [vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp]),

@@ -291,9 +291,9 @@ int64_t c2dsr_score_ce_tc_workspace_bytes(int64_t M, int64_t N, int d, int backw
     return ce_layout(nullptr, M, N, d, backward != 0).bytes + 1024;
 }
 
-int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
-                          int64_t M, int64_t N, int d, int passes, float* lse, float* loss_row, void* workspace,
-                          int64_t workspace_bytes, void* stream) {
+int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const uint16_t* W_hi, const uint16_t* W_lo, const float* bias,
+                          const float* zpad, const int64_t* gt, int64_t M, int64_t N, int d, int passes, float* lse,
+                          float* loss_row, void* workspace, int64_t workspace_bytes, void* stream) {
     if (M <= 0 || N <= 0) return C2DSR_OK;
     RUN(c2dsr_device_check());
     C2DSR_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
@@ -303,10 +303,15 @@ int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, con
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const CeLayout L = ce_layout(workspace, M, N, d, false);
+    CeLayout L = ce_layout(workspace, M, N, d, false);
     const bool split = passes == 3;
     RUN(split_rows(H, M, d, d, L.h_hi, split ? L.h_lo : nullptr, st));
-    RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
+    if (W_hi && (W_lo || !split)) {                 // the caller's split of W (shared by forward and backward)
+        L.w_hi = const_cast<uint16_t*>(W_hi);
+        L.w_lo = const_cast<uint16_t*>(W_lo);
+    } else {
+        RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
+    }
     tc::Maps maps;
     RUN(make_maps<kBN1>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
     tc::Problem pb{M, N, d, passes, 0, 1};
@@ -322,10 +327,10 @@ int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, con
     return check_launch("score_ce_fwd_tc");
 }
 
-int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
-                          const float* lse, const float* coef, int64_t M, int64_t N, int d, int passes, float* dH,
-                          float* dW, float* dbias, float* dzpad, void* workspace, int64_t workspace_bytes,
-                          void* stream) {
+int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, const uint16_t* W_lo, const float* bias,
+                          const float* zpad, const int64_t* gt, const float* lse, const float* coef, int64_t M,
+                          int64_t N, int d, int passes, float* dH, float* dW, float* dbias, float* dzpad,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
     if (M <= 0 || N <= 0) return C2DSR_OK;
     RUN(c2dsr_device_check());
     C2DSR_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
@@ -335,11 +340,16 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const float* bias, con
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const CeLayout L = ce_layout(workspace, M, N, d, true);
+    CeLayout L = ce_layout(workspace, M, N, d, true);
     const bool split = passes == 3;
     uint16_t* dz_lo = split ? L.dz_lo : nullptr;
     RUN(split_rows(H, M, d, d, L.h_hi, split ? L.h_lo : nullptr, st));
-    RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
+    if (W_hi && (W_lo || !split)) {
+        L.w_hi = const_cast<uint16_t*>(W_hi);
+        L.w_lo = const_cast<uint16_t*>(W_lo);
+    } else {
+        RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
+    }
     // 1. recompute the logits, emit dZ [M, N] as bf16 hi / lo
     {
         tc::Maps maps;

@@ -8,6 +8,30 @@
 
 namespace c2dsr {
 
+// 16-byte loads, 8-byte stores (d, ld_out multiples of 4, aligned pointers)
+__global__ void split_bf16_vec_kernel(const float* __restrict__ X, int64_t rows, int d, int64_t ld_out,
+                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    const int q = d >> 2;
+    const int64_t total = rows * (int64_t)q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / q;
+        const int c = (int)(i - r * q) << 2;
+        const float4 x = *reinterpret_cast<const float4*>(X + r * d + c);
+        uint16_t h[4], l[4];
+        split2(x.x, h[0], l[0]);
+        split2(x.y, h[1], l[1]);
+        split2(x.z, h[2], l[2]);
+        split2(x.w, h[3], l[3]);
+        uint2 ph, pl;
+        ph.x = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+        ph.y = (uint32_t)h[2] | ((uint32_t)h[3] << 16);
+        pl.x = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
+        pl.y = (uint32_t)l[2] | ((uint32_t)l[3] << 16);
+        *reinterpret_cast<uint2*>(hi + r * ld_out + c) = ph;
+        if (lo) *reinterpret_cast<uint2*>(lo + r * ld_out + c) = pl;
+    }
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ X, int64_t rows, int d, int64_t ld_out,
                                   uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const int64_t total = rows * (int64_t)d;
@@ -47,9 +71,12 @@ __global__ void split_bf16_T_kernel(const float* __restrict__ X, int64_t rows, i
 
 int split_rows(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo, cudaStream_t st) {
     if (rows <= 0) return C2DSR_OK;
-    int64_t blocks = ceil_div(rows * (int64_t)d, 256);
+    const bool vec = (d & 3) == 0 && (ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0;
+    int64_t blocks = ceil_div(rows * (int64_t)d, vec ? 1024 : 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    split_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, d, ld_out, hi, lo);
+    if (vec) split_bf16_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, d, ld_out, hi, lo);
+    else split_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(X, rows, d, ld_out, hi, lo);
     note_launches(1);
     return check_launch("split_bf16");
 }

@@ -431,8 +431,8 @@ class ScoreCETcFn(torch.autograd.Function):
         lse = torch.empty(M, device=dev, dtype=F32)
         loss_row = torch.empty(M, device=dev, dtype=F32)
         ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 0), dev)
-        call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, passes, ptr(lse),
-             ptr(loss_row), ptr(ws), ws.numel(), stream())
+        call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), None, None, ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, passes,
+             ptr(lse), ptr(loss_row), ptr(ws), ws.numel(), stream())
         loss = torch.empty((), device=dev, dtype=F32)
         call("c2dsr_wsum", ptr(loss_row), ptr(rowscale), M, ptr(loss), stream())
         ctx.save_for_backward(H, Hpad, W, b, wpad, gt, rowscale, zpad, lse)
@@ -451,8 +451,8 @@ class ScoreCETcFn(torch.autograd.Function):
         db = torch.zeros(N, device=dev, dtype=F32)
         dzpad = torch.empty(M, device=dev, dtype=F32)
         ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 1), dev)
-        call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d,
-             ctx.passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
+        call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), None, None, ptr(b), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M,
+             N, d, ctx.passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
         dHpad = torch.empty(M, d, device=dev, dtype=F32)
         gemm(0, 0, M, d, 1, dzpad, 1, wpad, d, dHpad, d)
         dwpad = torch.empty(1, d, device=dev, dtype=F32)
@@ -487,19 +487,23 @@ class DomainLossTcFn(torch.autograd.Function):
              stream())
         loss = torch.zeros((), device=dev, dtype=F32)
         lse = torch.empty(M, device=dev, dtype=F32)
+        # one bf16 hi / lo split of the classifier weights per step, shared by forward and backward
+        w_hi, w_lo = split_bf16(W, passes == 3) if M > 0 else (torch.empty(0, device=dev, dtype=BF16),) * 2
+        if w_lo is None:
+            w_lo = torch.empty(0, device=dev, dtype=BF16)
         if M > 0:
             loss_row = torch.empty(M, device=dev, dtype=F32)
             ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 0), dev)
-            call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt, I64), M, N, d, passes, ptr(lse),
-                 ptr(loss_row), ptr(ws), ws.numel(), stream())
+            call("c2dsr_score_ce_fwd_tc", ptr(H), ptr(W), ptr(w_hi), ptr(w_lo) if w_lo.numel() else None, ptr(b),
+                 ptr(zpad), ptr(gt, I64), M, N, d, passes, ptr(lse), ptr(loss_row), ptr(ws), ws.numel(), stream())
             call("c2dsr_wsum", ptr(loss_row), ptr(w), M, ptr(loss), stream())
-        ctx.save_for_backward(h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse)
+        ctx.save_for_backward(h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse, w_hi, w_lo)
         ctx.cfg = (R, M, passes)
         return loss
 
     @staticmethod
     def backward(ctx, d_loss):
-        h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse = ctx.saved_tensors
+        h_share, h_dom, W, b, wpad, perm, inv, H, gt, w, zpad, lse, w_hi, w_lo = ctx.saved_tensors
         R, M, passes = ctx.cfg
         B, L, d = h_share.shape
         N = W.shape[0]
@@ -511,8 +515,9 @@ class DomainLossTcFn(torch.autograd.Function):
         if M > 0:
             coef = (w * d_loss).contiguous()
             ws = workspace.get(query("c2dsr_score_ce_tc_workspace_bytes", M, N, d, 1), dev)
-            call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), ptr(b), ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d,
-                 passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad), ptr(ws), ws.numel(), stream())
+            call("c2dsr_score_ce_bwd_tc", ptr(H), ptr(W), ptr(w_hi), ptr(w_lo) if w_lo.numel() else None, ptr(b),
+                 ptr(zpad), ptr(gt), ptr(lse), ptr(coef), M, N, d, passes, ptr(dH), ptr(dW), ptr(db), ptr(dzpad),
+                 ptr(ws), ws.numel(), stream())
         d_share = torch.empty_like(h_share)
         d_dom = torch.empty_like(h_dom)
         dwpad = torch.empty(1, d, device=dev, dtype=F32)

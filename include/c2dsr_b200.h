@@ -187,16 +187,18 @@ int c2dsr_compact_rows(const int64_t* gt, int64_t M, int64_t ignore, int64_t* pe
 /* Tensor-core form of the two calls above (tcgen05 + TMA, bf16 hi/lo split with `passes` = 3 for
  * fp32-grade logits, 1 for plain bf16).  The fp32 logits are never written to HBM: the forward keeps
  * per-tile (max, sum-exp) pairs, the backward recomputes the logits, stores dZ as bf16 hi/lo and runs
- * dH = dZ W and dW += dZ^T H as two more tcgen05 GEMMs.  Both calls are self-contained (each splits
- * its own operands into `workspace`); backward = 1 sizes the workspace for the backward call. */
+ * dH = dZ W and dW += dZ^T H as two more tcgen05 GEMMs.  Both calls split their operands into
+ * `workspace`; W_hi / W_lo (optional, NULL = split here): the bf16 hi / lo split of W [N, d] made once by
+ * c2dsr_split_bf16 with ld_out = d, so that forward and backward of a step share it.  backward = 1 sizes the
+ * workspace for the backward call. */
 int64_t c2dsr_score_ce_tc_workspace_bytes(int64_t M, int64_t N, int d, int backward);
-int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
-                          int64_t M, int64_t N, int d, int passes, float* lse, float* loss_row, void* workspace,
-                          int64_t workspace_bytes, void* stream);
-int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const float* bias, const float* zpad, const int64_t* gt,
-                          const float* lse, const float* coef, int64_t M, int64_t N, int d, int passes, float* dH,
-                          float* dW, float* dbias, float* dzpad, void* workspace, int64_t workspace_bytes,
-                          void* stream);
+int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const uint16_t* W_hi, const uint16_t* W_lo, const float* bias,
+                          const float* zpad, const int64_t* gt, int64_t M, int64_t N, int d, int passes, float* lse,
+                          float* loss_row, void* workspace, int64_t workspace_bytes, void* stream);
+int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, const uint16_t* W_lo, const float* bias,
+                          const float* zpad, const int64_t* gt, const float* lse, const float* coef, int64_t M,
+                          int64_t N, int d, int passes, float* dH, float* dW, float* dbias, float* dzpad,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- K4b: full-catalogue scoring + rank count (evaluation) ---------------------------------
  * replaces the per-sample loop of Trainer.evaluate_batch (trainer.py:168-179):
