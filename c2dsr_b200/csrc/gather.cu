@@ -113,26 +113,39 @@ __global__ void item_rows_kernel(const float* __restrict__ dx, const int64_t* __
     }
 }
 
-// grid (chunks, feature slabs), block kSlab threads, dynamic smem (n_bins * kSlab floats).
-// bins 0 .. L-1: positional rows (unscaled g); bin L: the pad item row (scale * g).
+// grid (chunks, feature slabs), block (kSlab, kSub) threads, dynamic smem (kSub * n_bins * kSlab floats).
+// bins 0 .. L-1: positional rows (unscaled g); bin L: the pad item row (scale * g).  The chunk's tokens are
+// cut into kSub consecutive sub-ranges, one per threadIdx.y, each with its own bins (a quarter of the serial
+// chain of dependent loads); the kSub bin sets are then added in sub-range order = token order.
+constexpr int kSub = 4;            // (fewer, = blockDim.y, when len_max is too long for 4 bin sets in shared memory)
 __global__ void bin_partial_kernel(const float* __restrict__ dx, const int64_t* __restrict__ seq,
                                    const int64_t* __restrict__ pos, int64_t n_tok, int d, int L, int64_t pad,
                                    float scale, Dropout dr, float* __restrict__ partial) {
     extern __shared__ float bins[];
     const int n_bins = L + 1;
     const int f = blockIdx.y * kSlab + threadIdx.x;
-    for (int b = 0; b < n_bins; ++b) bins[b * kSlab + threadIdx.x] = 0.f;
-    const int64_t t0 = (int64_t)blockIdx.x * kTokChunk;
-    const int64_t t1 = t0 + kTokChunk < n_tok ? t0 + kTokChunk : n_tok;
+    float* mine = bins + (size_t)threadIdx.y * n_bins * kSlab;
+    for (int b = 0; b < n_bins; ++b) mine[b * kSlab + threadIdx.x] = 0.f;
+    const int n_sub = blockDim.y;
+    const int per = kTokChunk / n_sub;
+    const int64_t t0 = (int64_t)blockIdx.x * kTokChunk + threadIdx.y * per;
+    const int64_t t1 = t0 + per < n_tok ? t0 + per : n_tok;
     if (f < d) {
         for (int64_t t = t0; t < t1; ++t) {
             const float g = __ldg(dx + t * d + f) * drop_scale(dr, (uint64_t)t * d + f);
             const int64_t ps = pos[t];
-            if (ps >= 0 && ps < L) bins[ps * kSlab + threadIdx.x] += g;
-            if (seq[t] == pad) bins[L * kSlab + threadIdx.x] += scale * g;
+            if (ps >= 0 && ps < L) mine[ps * kSlab + threadIdx.x] += g;
+            if (seq[t] == pad) mine[L * kSlab + threadIdx.x] += scale * g;
         }
+    }
+    __syncthreads();
+    if (f < d) {
         float* out = partial + ((int64_t)blockIdx.x * n_bins) * d + f;
-        for (int b = 0; b < n_bins; ++b) out[(int64_t)b * d] = bins[b * kSlab + threadIdx.x];
+        for (int b = threadIdx.y; b < n_bins; b += n_sub) {
+            float s = 0.f;
+            for (int k = 0; k < n_sub; ++k) s += bins[((size_t)k * n_bins + b) * kSlab + threadIdx.x];
+            out[(int64_t)b * d] = s;
+        }
     }
 }
 
@@ -180,7 +193,9 @@ int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, fl
     if (n_tok <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(d > 0 && d <= 512, "d must be in (0, 512]");
     C2DSR_REQUIRE(n_tok < (1ll << 31) && n_rows > 0 && len_max > 0, "bad sizes");
-    const int smem = (len_max + 1) * kSlab * 4;
+    int n_sub = kSub;
+    while (n_sub > 1 && n_sub * (len_max + 1) * kSlab * 4 > 200 * 1024) n_sub >>= 1;
+    const int smem = n_sub * (len_max + 1) * kSlab * 4;
     C2DSR_REQUIRE(smem <= 200 * 1024, "len_max too large for the dense-bin reduction (<= 399)");
     if (workspace_bytes < c2dsr_gather_bwd_workspace_bytes(n_tok, d, n_rows, len_max)) {
         set_error("gather_bwd: workspace too small");
@@ -202,7 +217,7 @@ int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, fl
         attr = true;
     }
     const int64_t n_chunks = ceil_div(n_tok, kTokChunk);
-    bin_partial_kernel<<<dim3((unsigned)n_chunks, (unsigned)ceil_div(d, kSlab)), kSlab, smem, st>>>(
+    bin_partial_kernel<<<dim3((unsigned)n_chunks, (unsigned)ceil_div(d, kSlab)), dim3(kSlab, n_sub), smem, st>>>(
         dx, seq, pos, n_tok, d, len_max, pad_idx, scale, dr, partial);
     bin_reduce_kernel<<<(unsigned)ceil_div((int64_t)(len_max + 1) * d, 256), 256, 0, st>>>(partial, n_chunks, d,
                                                                                           len_max, pad_idx, d_P, d_hi);
