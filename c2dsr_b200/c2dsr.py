@@ -36,6 +36,7 @@ class SelfAttention(nn.Module):
         super().__init__()
         self.idx_pad = args.idx_pad
         self.n_head = args.n_head
+        self.n_layers = args.n_attn
         self.norm_first = bool(args.norm_first)
         self.p = args.dropout_attn
         # dense layers of the encoder: tcgen05 with the bf16 hi/lo split (3, default: products good to ~1e-6,
@@ -177,6 +178,36 @@ class C2DSR(nn.Module):
         return (self._branch(self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, s, 1),
                 self._branch(self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, s, 2),
                 self._branch(self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, s, 3))
+
+    @torch.no_grad()
+    def forward_select(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b, sel_share, sel_a, sel_b):
+        """Evaluation: (h_share[b, sel_share[b]], hx[b, sel_a[b]], hy[b, sel_b[b]]), each [B, d] -- the only rows
+        of forward() that Trainer.evaluate_batch reads.  With one encoder layer everything after the attention is
+        computed for that one position per sequence (ops.branch_select); otherwise forward() + a row gather."""
+        self._materialise()
+        if not (self.attn_share.n_layers == 1 and seq_share.is_cuda):
+            hs, hx, hy = self.forward(seq_share, seq_a, seq_b, pos_share, pos_a, pos_b)
+            ar = torch.arange(hs.shape[0], device=hs.device)
+            return hs[ar, sel_share], hx[ar, sel_a], hy[ar, sel_b]
+        cur = torch.cuda.current_stream()
+        if self._side is None or len(self._side) < 2:
+            self._side = tuple(torch.cuda.Stream() for _ in range(2))
+        jobs = ((self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, sel_share, None),
+                (self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, sel_a, self._side[0]),
+                (self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, sel_b, self._side[1]))
+        outs = [None] * 3
+        for i in (1, 2, 0):                                      # side streams first
+            attn, table, hi, seq, pos, sel, st = jobs[i]
+            st = st or cur
+            if st is not cur:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs[i] = ops.branch_select(hi, table.weight, attn.pos_emb.weight, seq, pos, sel,
+                                            float(self.d_latent ** 0.5), self.n_item - 1, attn.n_head, attn.norm_first,
+                                            attn.dense_passes_eval, attn.weights())
+        for st in self._side[:2]:
+            cur.wait_stream(st)
+        return tuple(outs)
 
     def forward_share(self, seq, pos):
         """models/C2DSR.py:79-85: the shared branch only (corrupted sequences)."""

@@ -95,7 +95,7 @@ __global__ void add_ln_fwd_kernel(const float* __restrict__ x, const float* __re
         const int f = lane + 32 * k;
         if (k < nper && f < d) out[t * d + f] = (v[k] - mean) * rstd * w[f] + b[f];
     }
-    if (lane == 0) {
+    if (lane == 0 && stats) {
         stats[2 * t] = mean;
         stats[2 * t + 1] = rstd;
     }
@@ -631,6 +631,66 @@ attn_seq_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ o, 
     }
 }
 
+// ---- evaluation: one query position per sequence ------------------------------------------------------------
+// Only h[b, sel[b]] is read from a branch at evaluation time (trainer.py:169-177).  In the LAST encoder layer every
+// token still contributes its key and value, but the query projection is only needed at sel[b], and everything
+// after the attention (output projection, residual + LayerNorm, feed-forward, LayerNorms) is per-token work that
+// is only needed for that one token: n_seq rows instead of n_seq * L.
+// warp per (sequence, head): soft-max attention of the single query sel[b] over the allowed keys j <= sel[b]
+__global__ void attn_select_kernel(const float* __restrict__ qkv, const int64_t* __restrict__ seq,
+                                   const int64_t* __restrict__ sel, AttnShape sh, float* __restrict__ o) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= sh.n_seq * sh.H) return;
+    const int h = (int)(w % sh.H);
+    const int64_t b = w / sh.H;
+    const int i = (int)sel[b];
+    const int nper = (sh.dh + 31) >> 5;
+    const int64_t ld = 3 * (int64_t)sh.d;
+    const int64_t ti = b * sh.L + i;
+    float q[kMaxPerLane], acc[kMaxPerLane];
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        q[k] = (k < nper && e < sh.dh) ? qkv[ti * ld + h * sh.dh + e] : 0.f;
+        acc[k] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j <= i; ++j) {
+        const int64_t tj = b * sh.L + j;
+        if (seq[tj] != sh.pad) continue;                                   // warp-uniform
+        const float* kj = qkv + tj * ld + sh.d + h * sh.dh;
+        const float* vj = kj + sh.d;
+        const float s = lane_dot(q, kj, sh.dh, nper, lane) * sh.scale;
+        const float m_new = fmaxf(m, s);
+        const float corr = expf(m - m_new);
+        const float pe = expf(s - m_new);
+        l = l * corr + pe;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int e = lane + 32 * k;
+            if (k < nper && e < sh.dh) acc[k] = acc[k] * corr + pe * vj[e];
+        }
+        m = m_new;
+    }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+        const int e = lane + 32 * k;
+        if (k < nper && e < sh.dh) o[b * sh.d + h * sh.dh + e] = acc[k] * inv;
+    }
+}
+
+// out[b, :] = x[b, sel[b], :]   (warp per sequence)
+__global__ void select_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ sel, int64_t n_seq, int L,
+                                   int d, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n_seq) return;
+    const float* src = x + (b * L + sel[b]) * d;
+    for (int e = lane; e < d; e += 32) out[b * d + e] = src[e];
+}
+
 static int seq_smem_bytes(const AttnShape& sh, bool bwd) {
     return ((bwd ? 4 : 3) * sh.L * sh.dh + (bwd ? 2 : 1) * sh.L * (sh.L + 1) + 2 * sh.L + 8) * 4;
 }
@@ -832,6 +892,77 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers, int n_layers, const flo
     }
     RUN(launch_add_ln(xlast, nullptr, lnf_w, lnf_b, nullptr, out, stf, T, d, 1, eps, none, st));
     return C2DSR_OK;
+}
+
+int64_t c2dsr_encoder_select_workspace_bytes(int64_t n_seq, int L, int d, int dense_passes) {
+    const int64_t T = n_seq * L;
+    return (4 * T + 6 * n_seq) * (int64_t)d * 4 + kGemmWsBytes + (dense_passes ? dense_tc_bytes(T, d) : 0) + 1024;
+}
+
+int c2dsr_encoder_fwd_select(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                             const float* x, const int64_t* seq, const int64_t* sel, int64_t n_seq, int L, int d,
+                             int n_head, int64_t pad_idx, int norm_first, int dense_passes, float eps, float* out,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(n_layers == 1, "the single-query forward covers one encoder layer (use c2dsr_encoder_fwd otherwise)");
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
+    C2DSR_REQUIRE(n_head > 0 && d % n_head == 0, "d must be divisible by n_head");
+    C2DSR_REQUIRE(dense_passes == 0 || dense_passes == 1 || dense_passes == 3, "dense_passes must be 0, 1 or 3");
+    if (workspace_bytes < c2dsr_encoder_select_workspace_bytes(n_seq, L, d, dense_passes)) {
+        set_error("encoder_fwd_select: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t T = n_seq * L, Td = T * d, Bd = n_seq * d;
+    float* s1 = (float*)workspace;              // [T, d]   pre-norm only: LayerNorm1(x)
+    float* qkv = s1 + Td;                       // [T, 3d]
+    float* x_sel = qkv + 3 * Td;                // [n_seq, d] each from here on
+    float* o_sel = x_sel + Bd;
+    float* y = o_sel + Bd;
+    float* x1 = y + Bd;
+    float* t1 = x1 + Bd;
+    float* t2 = t1 + Bd;
+    void* gws = t2 + Bd;
+    void* tws = (char*)gws + kGemmWsBytes;
+    const int64_t tws_bytes = dense_passes ? dense_tc_bytes(T, d) : 0;
+    const Dropout none = make_dropout(0.f, 0, 0);
+    const AttnShape sh = make_shape(n_seq, L, d, n_head, pad_idx);
+    const c2dsr_layer_weights& w = layers[0];
+    const float* attn_in = x;
+    if (norm_first) {
+        RUN(launch_add_ln(x, nullptr, w.ln1_w, w.ln1_b, nullptr, s1, nullptr, T, d, 1, eps, none, st));
+        attn_in = s1;
+    }
+    // keys and values of every token (and, for simplicity, every query: one GEMM)
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, T, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, qkv, 3 * d,
+              w.in_proj_b, 0, none, gws, kGemmWsBytes, st));
+    attn_select_kernel<<<(unsigned)ceil_div(n_seq * n_head, 8), 256, 0, st>>>(qkv, seq, sel, sh, o_sel);
+    select_rows_kernel<<<(unsigned)ceil_div(n_seq, 8), 256, 0, st>>>(x, sel, n_seq, L, d, x_sel);
+    note_launches(2);
+    // from here on: n_seq rows
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, n_seq, d, d, 1.f, o_sel, d, w.out_proj_w, d, 0.f, y, d, w.out_proj_b, 0,
+              none, gws, kGemmWsBytes, st));
+    const float* ffn_in;
+    if (norm_first) {
+        RUN(launch_add_ln(x_sel, y, nullptr, nullptr, nullptr, x1, nullptr, n_seq, d, 0, eps, none, st));
+        RUN(launch_add_ln(x1, nullptr, w.ln2_w, w.ln2_b, nullptr, t1, nullptr, n_seq, d, 1, eps, none, st));
+        ffn_in = t1;
+    } else {
+        RUN(launch_add_ln(x_sel, y, w.ln1_w, w.ln1_b, nullptr, x1, nullptr, n_seq, d, 1, eps, none, st));
+        ffn_in = x1;
+    }
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, n_seq, d, d, 1.f, ffn_in, d, w.lin1_w, d, 0.f, t2, d, w.lin1_b, 1, none, gws,
+              kGemmWsBytes, st));
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, n_seq, d, d, 1.f, t2, d, w.lin2_w, d, 0.f, y, d, w.lin2_b, 0, none, gws,
+              kGemmWsBytes, st));
+    float* last = t1;
+    if (norm_first) {
+        RUN(launch_add_ln(x1, y, nullptr, nullptr, nullptr, last, nullptr, n_seq, d, 0, eps, none, st));
+    } else {
+        RUN(launch_add_ln(x1, y, w.ln2_w, w.ln2_b, nullptr, last, nullptr, n_seq, d, 1, eps, none, st));
+    }
+    RUN(launch_add_ln(last, nullptr, lnf_w, lnf_b, nullptr, out, nullptr, n_seq, d, 1, eps, none, st));
+    return check_launch("encoder_fwd_select");
 }
 
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads* grads, int n_layers,

@@ -213,6 +213,25 @@ class EncoderFn(torch.autograd.Function):
         return (dx, None, None, None, None, None, None, None, None, *grads)
 
 
+@torch.no_grad()
+def branch_select(hi, E, P, seq, pos, sel, scale: float, pad_idx: int, n_head: int, norm_first: bool, dense_passes: int,
+                  weights):
+    """Evaluation form of one branch for a one-layer encoder: h[b, sel[b], :] only (no autograd, no dropout).
+    Gather for every token (keys and values need them all), then c2dsr_encoder_fwd_select."""
+    hi, E, P = _f(hi), _f(E), _f(P)
+    seq, pos, sel = seq.contiguous(), pos.contiguous(), sel.contiguous()
+    w = [_f(t) for t in weights]
+    n_seq, L = seq.shape
+    d = E.shape[1]
+    x = _gather_forward(hi, E, P, seq, pos, scale, 0.0, 0, 0)
+    out = torch.empty(n_seq, d, device=E.device, dtype=F32)
+    ws = workspace.get(query("c2dsr_encoder_select_workspace_bytes", n_seq, L, d, dense_passes), E.device)
+    table = _layer_table(w, 1)
+    call("c2dsr_encoder_fwd_select", C.addressof(table), 1, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(seq, I64), ptr(sel, I64),
+         n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, ptr(out), ptr(ws), ws.numel(), stream())
+    return out
+
+
 class BranchSetFn(torch.autograd.Function):
     """Several independent branches (K1 gather + K3 encoder each) as ONE autograd node that forks them
     onto CUDA streams and joins before returning, in forward and in backward.  One branch alone is too

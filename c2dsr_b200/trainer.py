@@ -336,11 +336,12 @@ class Trainer(object):
 
     def _encode_body(self, f):
         seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b, dom_b = f
-        h_share, hx, hy = self.model(seq_share, seq_a, seq_b, pos, pos_a, pos_b)
-        B, L = h_share.shape[0], h_share.shape[1]
-        ar = torch.arange(B, device=h_share.device)
-        pick = torch.where(dom_b.unsqueeze(-1), hy[ar, idx_b.view(-1) % L], hx[ar, idx_a.view(-1) % L])
-        return (h_share[:, -1] + pick).contiguous()
+        B, L = seq_share.shape
+        # only one position per sequence and branch is read: h_share[:, L-1], hx[:, idx_last_a], hy[:, idx_last_b]
+        last = torch.full((B,), L - 1, dtype=torch.int64, device=seq_share.device)
+        hs, hx, hy = self.model.forward_select(seq_share, seq_a, seq_b, pos, pos_a, pos_b, last, idx_a.view(-1) % L,
+                                               idx_b.view(-1) % L)
+        return (hs + torch.where(dom_b.unsqueeze(-1), hy, hx)).contiguous()
 
     def _encode_queries(self, f):
         """The three encoders of an evaluation batch; replayed from a CUDA graph from the second batch of a shape

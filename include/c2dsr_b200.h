@@ -122,6 +122,15 @@ int c2dsr_encoder_fwd(const c2dsr_layer_weights* layers_host, int n_layers, cons
                       const float* x, const int64_t* seq, int64_t n_seq, int L, int d, int n_head, int64_t pad_idx,
                       int norm_first, int dense_passes, float eps, float p, uint64_t seed, uint64_t tag, float* out,
                       float* saved, void* workspace, int64_t workspace_bytes, void* stream);
+/* Evaluation form for a ONE-layer encoder: only out[b, :] = encoder(x)[b, sel[b], :] is produced (the position
+ * the ranking query reads, trainer.py:169-177).  Keys / values are projected for every token; the attention
+ * runs for the single query sel[b]; output projection, residuals, LayerNorms and the feed-forward run on n_seq
+ * rows instead of n_seq * L.  No dropout, nothing saved.  Same numbers as c2dsr_encoder_fwd + a row gather. */
+int64_t c2dsr_encoder_select_workspace_bytes(int64_t n_seq, int L, int d, int dense_passes);
+int c2dsr_encoder_fwd_select(const c2dsr_layer_weights* layers_host, int n_layers, const float* lnf_w,
+                             const float* lnf_b, const float* x, const int64_t* seq, const int64_t* sel, int64_t n_seq,
+                             int L, int d, int n_head, int64_t pad_idx, int norm_first, int dense_passes, float eps,
+                             float* out, void* workspace, int64_t workspace_bytes, void* stream);
 /* Gradients are ACCUMULATED (+=) into `grads` and lnf grads; dx is overwritten. */
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers_host, const c2dsr_layer_grads* grads_host, int n_layers,
                       const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,

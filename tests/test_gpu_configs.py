@@ -120,3 +120,26 @@ def test_million_item_style_sharded_eval():
     ref = (Q.double() @ W.double().t())
     ref_rank = (ref > ref[torch.arange(n_q), gt].unsqueeze(1)).sum(1)
     assert float((counts.cpu() - ref_rank.cpu()).abs().float().mean()) < 0.5     # near-tie flips only
+
+
+@pytest.mark.parametrize("d,L,n_head,norm_first", [(256, 15, 1, False), (128, 30, 2, True), (64, 50, 4, False)])
+def test_forward_select_equals_forward(d, L, n_head, norm_first):
+    """Evaluation reads one position per sequence and branch; C2DSR.forward_select computes only that row after the
+    attention of a one-layer encoder.  It must equal forward() followed by the row gather."""
+    tr, otr, batch, ebatch = _setup(d, L, n_head, 1, 16, norm_first=norm_first)
+    m = tr.model
+    m.eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        m.convolve_graph()
+        b = tuple(x.to(DEV) for x in ebatch[:6])
+        B = b[0].shape[0]
+        sels = [torch.randint(0, L, (B,), generator=g).to(DEV) for _ in range(3)]
+        sels[0][:] = L - 1
+        full = m(*b)
+        ar = torch.arange(B, device=DEV)
+        want = [h[ar, s] for h, s in zip(full, sels)]
+        got = m.forward_select(*b, *sels)
+    for a, c, nm in zip(got, want, ("share", "a", "b")):
+        assert a.shape == c.shape
+        assert float((a - c).abs().max()) <= 2e-5 * float(c.abs().max()), nm
