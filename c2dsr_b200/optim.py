@@ -25,6 +25,8 @@ class FusedAdamW(torch.optim.Optimizer):
     and ~1 GB of traffic per step at the Food-Kitchen shape).  ``zero_grad()`` clears the sums;
     ``accumulated_grad(p)`` returns what ``p.grad`` holds in the reference at the same point."""
 
+    BIG = 1 << 20            # elements: tensors at least this large go into the first launch
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, amsgrad=True,
                  accumulate=False):
         if not amsgrad:
@@ -128,6 +130,9 @@ class FusedAdamW(torch.optim.Optimizer):
         return loss
 
     def _launch(self, gi, group, items, step_no):
+        # large tensors first: the table is launched in two parts (grid = chunks of the largest tensor x tensors),
+        # so that the ~50 small tensors do not each pay for a grid sized for the embedding tables
+        items = sorted(items, key=lambda it: -it[0].numel())
         key = (gi, step_no == 0, tuple((p.data_ptr(), g.data_ptr()) for p, g, _ in items))
         dev = items[0][0].device
         capturing = torch.cuda.is_current_stream_capturing()
@@ -156,13 +161,18 @@ class FusedAdamW(torch.optim.Optimizer):
             self._table_dev = table
             self._table_key = None if capturing else key
             self._table_n = n
-            self._table_max = max(p.numel() for p, _, _ in items)
+            n_big = sum(1 for p, _, _ in items if p.numel() >= self.BIG)
+            self._table_parts = [(0, n_big, items[0][0].numel())] if n_big else []
+            if n_big < n:
+                self._table_parts.append((n_big, n - n_big, items[n_big][0].numel()))
         b1, b2 = group["betas"]
-        if self.dyn_state is not None:
-            if not torch.cuda.is_current_stream_capturing():
-                self.sync_lr()
-            call("c2dsr_adamw_amsgrad_dyn", ptr(self._table_dev), self._table_n, self._table_max, ptr(self.dyn_state),
-                 b1, b2, group["eps"], group["weight_decay"], stream())
-            return
-        call("c2dsr_adamw_amsgrad", ptr(self._table_dev), self._table_n, self._table_max, float(group["lr"]), b1, b2,
-             group["eps"], group["weight_decay"], step_no, stream())
+        if self.dyn_state is not None and not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
+        for first, count, max_n in self._table_parts:
+            tab = ptr(self._table_dev) + first * C.sizeof(AdamTensor)
+            if self.dyn_state is not None:
+                call("c2dsr_adamw_amsgrad_dyn", tab, count, max_n, ptr(self.dyn_state), b1, b2, group["eps"],
+                     group["weight_decay"], stream())
+            else:
+                call("c2dsr_adamw_amsgrad", tab, count, max_n, float(group["lr"]), b1, b2, group["eps"],
+                     group["weight_decay"], step_no, stream())
