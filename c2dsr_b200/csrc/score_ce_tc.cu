@@ -225,7 +225,8 @@ struct CeLayout {       // carve-up of the caller's workspace
     uint16_t *h_hi, *h_lo, *w_hi, *w_lo;    // [M, d], [N, d]
     uint16_t *dz_hi, *dz_lo;                // [M, ldn]
     float *pmax, *psum, *zgt;
-    float* slabs;                           // split-K partial sums of the gradient GEMMs / db partials
+    float* slabs;                           // split-K partial sums of the gradient GEMMs
+    float* db_part;                         // chunk partials of the dZ column sums (own buffer: runs beside the GEMMs)
     int64_t ldn, n_pairs, bytes;
     int ks_dh, ks_dw;
 };
@@ -245,7 +246,7 @@ static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, bool backward) 
     L.pmax = (float*)take(M * L.n_pairs * 4); L.psum = (float*)take(M * L.n_pairs * 4);
     L.zgt = (float*)take(M * 4);
     L.dz_hi = L.dz_lo = nullptr;
-    L.slabs = nullptr;
+    L.slabs = L.db_part = nullptr;
     // K slabs: enough tiles to fill the SMs, and short accumulation chains in tensor memory
     const int64_t tiles_dh = ceil_div(M, tc::BM) * ceil_div(d, kBN2), tiles_dw = ceil_div(N, tc::BM) * ceil_div(d, kBN2);
     auto pick = [](int64_t tiles, int64_t K) {
@@ -263,8 +264,8 @@ static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, bool backward) 
         L.dz_hi = (uint16_t*)take(M * L.ldn * 2); L.dz_lo = (uint16_t*)take(M * L.ldn * 2);
         int64_t f = (int64_t)L.ks_dh * M * d;
         if ((int64_t)L.ks_dw * N * d > f) f = (int64_t)L.ks_dw * N * d;
-        if (ceil_div(M, kDbChunk) * N > f) f = ceil_div(M, kDbChunk) * N;
         L.slabs = (float*)take(f * 4);
+        L.db_part = (float*)take(ceil_div(M, kDbChunk) * N * 4);
     }
     L.bytes = p - (char*)ws;
     return L;
@@ -283,6 +284,35 @@ using namespace c2dsr;
 static unsigned ew_grid(int64_t n) {
     const int64_t b = ceil_div(n, 256);
     return (unsigned)(b < 2368 ? (b > 0 ? b : 1) : 2368);
+}
+
+// One helper stream + two events per device and host thread, created on first use (never during a stream capture:
+// the first call of a process is an eager one).  Only used for work that is forked from and joined back into the
+// caller's stream inside a single entry point.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    int device = -1;
+    bool ok = false;
+};
+static SideStream& side_stream() {
+    static thread_local SideStream tab[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStream& s = tab[dev & 15];
+    if (s.device != dev) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        s.ok = false;
+        s.device = dev;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
+            s.ok = true;
+        else
+            cudaGetLastError();
+        (void)cap;
+    }
+    return s;
 }
 
 extern "C" {
@@ -362,6 +392,24 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
             RUN((launch_gemm<kBN1, kStages1, false, false, false>(maps, pb, epi, st)));
         }
     }
+    // db[N] += column sums of dZ, and dzpad: HBM-bound reads of dZ that depend on nothing but step 1.  They run
+    // on a side stream next to the two tensor-core GEMMs below (one persistent GEMM CTA per SM leaves room for
+    // them) and are joined before returning; the fork / join are event edges, so they are captured like the rest.
+    SideStream& side = side_stream();
+    if (side.ok) {
+        cudaEventRecord(side.fork, st);
+        cudaStreamWaitEvent(side.stream, side.fork, 0);
+    }
+    {
+        cudaStream_t s2 = side.ok ? side.stream : st;
+        const int64_t n_chunks = ceil_div(M, kDbChunk);
+        dz_colsum_partial_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)n_chunks), 256, 0, s2>>>(
+            L.dz_hi, dz_lo, M, N, L.ldn, L.db_part);
+        dz_colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, s2>>>(L.db_part, n_chunks, N, dbias);
+        dzpad_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, s2>>>(zpad, lse, coef, gt, M, N, dzpad);
+        note_launches(3);
+        if (side.ok) cudaEventRecord(side.join, side.stream);
+    }
     // 2. dH[M, d] = dZ[M, N] W[N, d]: A = dZ (K-major, K = N), B = W read MN-major from its [N, d] storage
     {
         tc::Maps maps;
@@ -382,15 +430,7 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
         slab_reduce_kernel<<<ew_grid(N * (int64_t)d), 256, 0, st>>>(L.slabs, L.ks_dw, N * (int64_t)d, dW, 1);
         note_launches(1);
     }
-    // 4. db[N] += column sums of dZ; dzpad
-    {
-        const int64_t n_chunks = ceil_div(M, kDbChunk);
-        dz_colsum_partial_kernel<<<dim3((unsigned)ceil_div(N, 256), (unsigned)n_chunks), 256, 0, st>>>(
-            L.dz_hi, dz_lo, M, N, L.ldn, L.slabs);
-        dz_colsum_final_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(L.slabs, n_chunks, N, dbias);
-        dzpad_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(zpad, lse, coef, gt, M, N, dzpad);
-        note_launches(3);
-    }
+    if (side.ok) cudaStreamWaitEvent(st, side.join, 0);
     return check_launch("score_ce_bwd_tc");
 }
 
