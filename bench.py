@@ -31,6 +31,7 @@ WORKLOADS = {
     "fk": dict(shape="fk", d_latent=256, batch_size=256, batch_size_eval=2048),
     "mb": dict(shape="mb", d_latent=256, batch_size=256, batch_size_eval=2048),
     "ee": dict(shape="ee", d_latent=128, batch_size=512, batch_size_eval=2048),
+    "tiny": dict(shape="tiny", d_latent=32, batch_size=32, batch_size_eval=64),      # contract tests only
 }
 
 

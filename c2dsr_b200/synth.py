@@ -21,6 +21,8 @@ SHAPES = {
                len_max=15, frac_a=0.50),
     "ee": dict(dataset="Entertainment-Education", n_item_a=8367, n_item_b=11404, n_train=120635, n_val=6929,
                n_test=6785, len_max=30, frac_a=0.50),
+    "tiny": dict(dataset="Synthetic-tiny", n_item_a=1500, n_item_b=2500, n_train=600, n_val=64, n_test=64,
+                 len_max=15, frac_a=0.48),
     "1m": dict(dataset="Synthetic-1M", n_item_a=400000, n_item_b=600000, n_train=0, n_val=8192, n_test=8192,
                len_max=15, frac_a=0.45),
 }

@@ -94,3 +94,21 @@ def test_main_flags_cover_reference():
     assert ref_flags <= {n.lstrip("-") for n, _ in FLAGS}
     defaults = {n.lstrip("-"): kw.get("default") for n, kw in FLAGS}
     assert (defaults["d_latent"], defaults["batch_size"], defaults["seed"], defaults["l2"]) == (128, 512, 3407, 5e-4)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port on the host cores) prints the driver's JSON line: same
+    metric / unit as the GPU arm, impl = reference, e2e without transfers, cpu_baseline describing the run."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    z = json.loads(r.stdout.strip().splitlines()[-1])
+    assert z["impl"] == "reference" and z["metric"] == "train_seqs_per_sec" and z["unit"] == "seq/s"
+    assert z["value"] > 0 and z["higher_is_better"] is True and z["n_gpus"] == 1 and z["steps"] == 1
+    assert z["e2e"] == {"value": z["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = z["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == z["value"] and "sample" in cb
+    assert "workload" in z["config"]
