@@ -215,3 +215,26 @@ def test_full_size_food_kitchen_eval_properties():
         Sr = ops.score_shard(Q, W[n0:n1], b[n0:n1])
         ops.rank_from_scores(Sr, s_gt, gt, None, n0, n1, counts)
     assert torch.equal(counts, full)
+
+
+def test_bench_json_contract_on_gpu():
+    """`python bench.py` on a tiny workload: one JSON line with every key of the driver's contract, measured through
+    the CUDA path (kernel launches counted, the training step replayed from its graph)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "tiny", "--steps", "4",
+                        "--warmup", "1", "--no-cpu-baseline", "--eval-batches", "2"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    z = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "eval"):
+        assert k in z, k
+    assert z["metric"] == "train_seqs_per_sec" and z["unit"] == "seq/s" and z["steps"] == 4 and z["value"] > 0
+    assert z["gpu_launches"] > 0 and z["config"]["cuda_graph_steps"] is True and "workload" in z["config"]
+    assert set(z["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and z["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(z["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert z["eval"]["value"] > 0
