@@ -197,9 +197,11 @@ int gemm_dispatch(int ta, int tb, int64_t M, int64_t N, int64_t K, float alpha, 
     const int bm = small ? 64 : 128;
     const int64_t tiles = ceil_div(M, bm) * ceil_div(N, bm);
     int splits = 1;
-    if (tiles < 120 && K >= 512 && workspace) {
+    // few output tiles: cut K into slabs (added in slab order by a second kernel) so that more than a handful of
+    // SMs work -- also for the short K = 256 products of the infomax block (16 tiles of 64 x 64 otherwise)
+    if (((tiles < 120 && K >= 512) || (tiles < 40 && K >= 256)) && workspace) {
         splits = (int)ceil_div(296, tiles);
-        const int64_t max_by_k = K / 128;
+        const int64_t max_by_k = K >= 512 ? K / 128 : K / 64;
         if (splits > max_by_k) splits = (int)max_by_k;
         if (splits > 64) splits = 64;
         while (splits > 1 && (int64_t)splits * M * N * 4 > workspace_bytes) --splits;
