@@ -112,3 +112,16 @@ def test_bench_reference_arm_contract():
     cb = z["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == z["value"] and "sample" in cb
     assert "workload" in z["config"]
+
+
+def test_header_is_plain_c():
+    """include/c2dsr_b200.h is the drop-in boundary: it must compile as C99 (no C++ or torch types) and as C++."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "c2dsr_b200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
