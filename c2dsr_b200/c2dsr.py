@@ -120,6 +120,7 @@ class C2DSR(nn.Module):
         self._gcn_lazy = None
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
+        self._share_calls = 0           # forward_share() calls since convolve_graph(): each gets its own dropout tag
 
     def _apply(self, fn, *a, **k):
         """.to()/.cuda(): the CSR graphs follow the parameters; cached propagations are dropped."""
@@ -142,6 +143,7 @@ class C2DSR(nn.Module):
         ``lazy=True`` (Trainer.train_step): only fix the step's seed; the three propagations are then computed
         by the branches that consume them, each on its own stream, inside forward_all (and cached as usual)."""
         s = self._next_seed()
+        self._share_calls = 0
         if lazy and self.branch_streams and torch.is_grad_enabled() and self.embed_i.weight.is_cuda \
                 and self.gnn_share.n_gnn >= 1:
             self._gcn_lazy = s
@@ -212,7 +214,11 @@ class C2DSR(nn.Module):
     def forward_share(self, seq, pos):
         """models/C2DSR.py:79-85: the shared branch only (corrupted sequences)."""
         self._materialise()
-        return self._branch(self.attn_share, self.embed_i, self.hi_share, seq, pos, self._next_seed(), 4)
+        # with the device-resident per-step key every call of a step sees the same seed: the call counter keeps the
+        # masks of the corrupted-A and corrupted-B passes (trainer.py:105,108) different
+        tag = 4 + self._share_calls
+        self._share_calls += 1
+        return self._branch(self.attn_share, self.embed_i, self.hi_share, seq, pos, self._next_seed(), tag)
 
     def forward_all(self, seq_share, seq_a, seq_b, pos_share, pos_a, pos_b, seq_neg_a, seq_neg_b):
         """The five branches of a training step; the three that go through ``attn_share`` (clean,

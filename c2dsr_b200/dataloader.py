@@ -194,6 +194,24 @@ class CDSRDataset(torch.utils.data.Dataset):
             cache[key] = (torch.stack((a, b), 1), na, nb)
         return cache[key]
 
+    def check_bounds(self, n_item: int):
+        """The kernels index E[seq] and P[pos] without bounds checks; the reference would raise IndexError from
+        nn.Embedding (a sequence of len_max + 1 items gives pos == len_max).  Checked once per split, on the host.
+        Also reports how many sequences start with a real item: their leading query rows have no allowed key under
+        the reference's inverted key-padding mask -- the reference produces NaN there with an even
+        head count in eval mode, this implementation defines the row as 0."""
+        seqs, poss = self.fields[0:3], self.fields[3:6]
+        hi_seq = max(int(x.max()) for x in seqs) if self.length else 0
+        lo_seq = min(int(x.min()) for x in seqs) if self.length else 0
+        hi_pos = max(int(x.max()) for x in poss) if self.length else 0
+        if lo_seq < 0 or hi_seq >= n_item:
+            raise IndexError(f"{self.mode} split: item id out of range [0, {n_item}) (min {lo_seq}, max {hi_seq})")
+        if hi_pos >= self.len_max:
+            raise IndexError(f"{self.mode} split: position {hi_pos} >= len_max = {self.len_max} "
+                             "(a sequence longer than len_max items; the reference raises IndexError here too)")
+        self.n_fully_masked = int((self.fields[0][:, 0] != n_item - 1).sum()) if self.length else 0
+        return self.n_fully_masked
+
     def to(self, device, pin: bool = False):
         """Make the whole split device-resident (or pinned) once -- 'next' row f-1."""
         if pin and torch.device(device).type == "cpu":
@@ -219,6 +237,8 @@ class Batch(tuple):
     for a device-resident training split, the one ``[14, B, L]`` tensor its fields are views of (``packed``)."""
     n_valid = None
     packed = None
+    global_rows = None      # rows the ranks process together in this step (the loss normaliser under data parallelism)
+    global_batch = None     # samples of the global batch (differs from global_rows when a short batch is replicated)
 
 
 class BatchLoader:
@@ -258,9 +278,17 @@ class BatchLoader:
             counts, na, nb = self.dataset.valid_counts(self.len_rec, na, nb)
         for lo in range(0, n, self.batch_size):
             hi = min(lo + self.batch_size, n)
+            g_batch = g_rows = hi - lo
             if self.world_size > 1:                     # data-parallel: contiguous slice of the global batch
                 per = (hi - lo + self.world_size - 1) // self.world_size
-                lo, hi = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
+                if per * (self.world_size - 1) >= hi - lo:
+                    # a remainder so short that some rank would get nothing: every rank takes all of it.  The
+                    # all-reduced normalisers (valid-target counts, rows) come out world x larger, so each rank
+                    # contributes loss / world and gradient / world and the sums over ranks are the single-
+                    # process values; no rank ever runs an empty step or skips a collective
+                    g_rows = (hi - lo) * self.world_size
+                else:
+                    lo, hi = min(lo + self.rank * per, hi), min(lo + (self.rank + 1) * per, hi)
             stacked = getattr(self.dataset, "stacked", None)
             if order is None:
                 if stacked is not None:
@@ -281,6 +309,7 @@ class BatchLoader:
                     out = Batch(x.index_select(0, idx) for x in self.dataset.fields)
                 if counts is not None:
                     out.n_valid = (tuple(int(v) for v in counts.index_select(0, order[lo:hi]).sum(0)), na, nb)
+            out.global_rows, out.global_batch = g_rows, g_batch
             yield out
 
 

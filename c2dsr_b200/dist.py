@@ -2,8 +2,10 @@
 box, gloo in the CPU tests).  The path has exactly two exchange steps:
 
 * training  -- data-parallel: the global batch is split across ranks, parameters and graph are
-  replicated; per step one tiny integer all-reduce (valid-target counts, so that loss
-  normalisers equal the single-GPU ones) and one sum all-reduce of the fp32 gradients;
+  replicated; per step one tiny all-reduce (valid-target counts and rows, so that loss normalisers
+  equal the single-GPU ones), then a sharded optimiser step (``FlatShards``): the fp32 gradients are
+  reduce-scattered, every rank runs AdamW on its 1/world of one flat parameter buffer, and the
+  updated shards are all-gathered (same bytes on the wire as one all-reduce);
 * evaluation -- each rank encodes its slice of the query batch and the query vectors are
   all-gathered (2 MB); the item catalogue is sharded by rows of the classifier; the target score
   comes from the owning shard (sum all-reduce with zeros elsewhere, exact) and the per-shard partial
@@ -12,7 +14,7 @@ box, gloo in the CPU tests).  The path has exactly two exchange steps (SURVEY.md
 from __future__ import annotations
 
 import os
-from typing import Dict, Iterable, List, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist
@@ -71,36 +73,6 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-class GradBucket:
-    """Flat fp32 buffer holding a copy of every live gradient, all-reduced in one call.
-
-    Each step's local gradients are summed over the ranks; the optimiser adds the reduced views to its
-    per-epoch gradient sums (reference semantics: gradients accumulate across the batches of an epoch,
-    trainer.py:42 vs :157; all-reduce is linear, so the order of the two sums does not matter).
-    """
-
-    def __init__(self):
-        self.flat = None
-        self.layout = None
-
-    def reduce(self, params: Iterable[torch.nn.Parameter]) -> Dict[torch.nn.Parameter, torch.Tensor]:
-        live = [p for p in params if p.grad is not None]
-        layout = tuple((id(p), p.numel()) for p in live)
-        total = sum(n for _, n in layout)
-        if self.layout != layout:
-            self.flat = torch.empty(total, dtype=torch.float32, device=live[0].device)
-            self.layout = layout
-        views, o = {}, 0
-        for p in live:
-            n = p.numel()
-            v = self.flat[o:o + n].view_as(p)
-            v.copy_(p.grad)
-            views[p] = v
-            o += n
-        allreduce_sum_(self.flat)
-        return views
-
-
 class FlatShards:
     """Sharded optimiser step for data-parallel training (ZeRO-1 style; same bytes on the wire as one
     all-reduce, but every rank runs AdamW on 1/world of the parameters instead of all of them -- the update is
@@ -141,7 +113,10 @@ class FlatShards:
 
     def reduce_scatter_grads(self) -> torch.Tensor:
         """bucket <- this step's gradients; grad_shard <- sum over ranks of bucket[shard of this rank]."""
-        torch._foreach_copy_(self.views, [p.grad for p in self.params])
+        # a parameter of the frozen layout that got no gradient this step (e.g. a classifier whose domain has no
+        # valid row in this rank's shard) contributes zeros -- never a missing collective operand
+        torch._foreach_copy_(self.views, [p.grad if p.grad is not None else torch.zeros_like(v)
+                                          for p, v in zip(self.params, self.views)])
         if dist.get_backend() == "gloo":                     # CPU tests: gloo has no reduce-scatter
             dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM)
             self.grad_shard.copy_(self.bucket[self.rank * self.shard:(self.rank + 1) * self.shard])

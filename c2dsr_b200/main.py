@@ -115,6 +115,7 @@ def main(argv=None):
             noter.log_msg(f"\t| lr    | from {lr_seen:.2e} | to {lr_now:.2e} |")
             lr_seen = lr_now
     noter.log_final_result(epoch, best_val, res_test)
+    main.last_trainer = trainer            # (tests compare the trained model's ranks with the oracle)
     return best_val, res_test
 
 

@@ -20,7 +20,7 @@ from . import _cabi, dist as cdist
 from ._cabi import DynSeed, call, ptr, query, stream, workspace
 from . import ops
 from .c2dsr import C2DSR
-from .dataloader import get_dataloader
+from .dataloader import Batch, get_dataloader
 from .graph import make_graph, make_graph_device
 from .optim import FusedAdamW
 
@@ -54,6 +54,12 @@ class Trainer(object):
                                     weight_decay=args.l2, amsgrad=True, accumulate=True)
         self.scheduler = torch.optim.lr_scheduler.StepLR(self.optimizer, step_size=args.lr_step, gamma=args.lr_gamma)
         self.noter = noter
+        for ld in (self.trainloader, self.valloader, self.testloader):
+            if ld is not None and hasattr(ld.dataset, "check_bounds"):
+                n_masked = ld.dataset.check_bounds(args.n_item)
+                if n_masked and noter is not None and hasattr(noter, "log_msg"):
+                    noter.log_msg(f"\t| note  | {ld.dataset.mode}: {n_masked} sequences start with a real item; their "
+                                  "leading query rows have no allowed key (reference: NaN-prone, here: 0)")
         if getattr(args, "data_on_device", True):
             for ld in (self.trainloader, self.valloader, self.testloader):
                 if ld is not None and hasattr(ld.dataset, "to"):
@@ -73,7 +79,6 @@ class Trainer(object):
         # skip loss rows whose target is ignore_index (exactly zero contribution); off = every row, like the reference
         self.skip_ignored = bool(getattr(args, "skip_ignored_rows", True))
         self._wsplit = {}
-        self.bucket = cdist.GradBucket()
         self.shards = None           # data-parallel: flat parameter buffer + sharded optimiser step (lazy)
         # per-step device state: optimiser step number, learning rate and dropout key words (header:
         # c2dsr_step_state).  Eager and replayed steps read the same state, so they compute the same thing.
@@ -108,7 +113,8 @@ class Trainer(object):
         t_start = time.time()
         for batch in self.trainloader:
             losses = self.train_step(batch)
-            sums += torch.stack(losses).detach() * (batch[0].shape[0] * self.world_size)
+            sums += torch.stack(losses).detach() * (getattr(batch, "global_batch", None)
+                                                    or batch[0].shape[0] * self.world_size)
         loss_tr, loss_rec, loss_mi = (sums / max(self.n_tr, 1)).tolist()    # one host sync per epoch
         self.noter.log_train(loss_tr, loss_rec, loss_mi, time.time() - t_start)
 
@@ -142,6 +148,8 @@ class Trainer(object):
     def losses(self, batch):
         """Forward part of trainer.py:91-154 -> (loss, loss_rec, loss_mi), differentiable."""
         n_valid = self._caps if self._caps is not None else self._valid_rows(batch)
+        # rows all ranks process in this step, known on the host (the loader's bookkeeping); equal shards otherwise
+        g_rows = getattr(batch, "global_rows", None) or batch[0].shape[0] * self.world_size
         (seq_share, seq_a, seq_b, pos, pos_a, pos_b, gt_share_a, gt_share_b, gt_a, gt_b, gt_mask_a, gt_mask_b,
          seq_neg_a, seq_neg_b) = (x.to(self.device, non_blocking=True) for x in batch)
         m = self.model
@@ -156,7 +164,7 @@ class Trainer(object):
         n_a, n_b, b_glob = counts[0], counts[1], counts[2]
 
         loss_mi = ops.InfomaxFn.apply(h_share, hx, hy, h_neg_a, h_neg_b, m.D_a.weight, m.D_b.weight, m.D_a.bias,
-                                      m.D_b.bias, gt_mask_a, gt_mask_b, 1.0 / (B * self.world_size))
+                                      m.D_b.bias, gt_mask_a, gt_mask_b, 1.0 / g_rows)
 
         if self.score_path == "tc":
             # row assembly + tcgen05 logits / cross-entropy as one node per domain (ops.DomainLossTcFn)
@@ -186,8 +194,8 @@ class Trainer(object):
                 # rows whose target is the ignore class add nothing to the loss or to any gradient: run the
                 # catalogue-wide GEMMs on the other rows only (a stable partition brings them to the front)
                 mv = n_valid[k]
-                if mv == 0:
-                    parts.append(hs.sum() * 0.0)
+                if mv == 0:                 # zero loss, and zero (not missing) gradients for the classifier
+                    parts.append((hs.sum() + cls.weight.sum() + cls.bias.sum()) * 0.0)
                     continue
                 keep = ops.compact_rows(gt, cls.weight.shape[0])[:mv]
                 H, Hpad, gt, w = H.index_select(0, keep), Hpad.index_select(0, keep), gt[keep], w[keep]
@@ -246,7 +254,8 @@ class Trainer(object):
             self.model.convolve_graph(lazy=True)
             return self.train_batch(batch)
         nv = self._valid_rows(batch) if self.skip_ignored else None
-        key = (tuple(batch[0].shape), nv is not None)
+        # (the infomax normaliser 1 / global rows is baked into the captured launch: part of the key)
+        key = (tuple(batch[0].shape), nv is not None, getattr(batch, "global_rows", None))
         g = self._graphs.get(key)
         if g is None:
             seen = self._warm.setdefault(key, [])
@@ -304,7 +313,10 @@ class Trainer(object):
         try:
             with torch.cuda.graph(graph):
                 self.model.convolve_graph(lazy=True)
-                out = torch.stack(self.train_batch(static))
+                step_in = Batch(static)             # carries the host-side normaliser facts of the captured shape
+                step_in.global_rows = getattr(batch, "global_rows", None)
+                step_in.global_batch = getattr(batch, "global_batch", None)
+                out = torch.stack(self.train_batch(step_in))
         finally:
             self._caps = None
         g = dict(graph=graph, static=static, out=out, caps=caps or (2 * B * R, 2 * B * R),

@@ -8,7 +8,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-GOLDEN_NAMES = ("tiny_default", "tiny_deep", "tiny_prenorm_shared")
+GOLDEN_NAMES = ("tiny_default", "tiny_deep", "tiny_prenorm_shared", "mid_default")
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 

@@ -1,5 +1,5 @@
 """world_size = 2 checks of the multi-GPU host logic on CPU (gloo): catalogue sharding with
-partial rank counts, the data-parallel gradient bucket and the global loss normalisers.  The
+partial rank counts, the sharded optimiser step, uneven data-parallel batches and the global loss normalisers.  The
 per-rank compute is done by the oracle here (there is no GPU); the exchange logic under test is
 the code the CUDA path uses (c2dsr_b200/dist.py)."""
 import os
@@ -75,18 +75,34 @@ def _worker(rank, world, port, ret):
     cdist.allreduce_sum_(counts)
     ok &= bool(np.array_equal(counts.numpy() + 1, ref))
 
-    # --- gradient bucket: accumulated local grads -> accumulated global grads, dead params skipped ---
-    ps = [torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2))]
-    ps[0].grad = torch.full((4, 3), float(rank + 1))
-    ps[1].grad = torch.arange(5.0) * (rank + 1)
-    bucket = cdist.GradBucket()
-    views = bucket.reduce(ps)
-    ok &= ps[2] not in views
-    ok &= bool(torch.equal(views[ps[0]], torch.full((4, 3), 3.0)))
-    ok &= bool(torch.equal(views[ps[1]], torch.arange(5.0) * 3))
-    ok &= bool(torch.equal(ps[0].grad, torch.full((4, 3), float(rank + 1))))     # local accumulators untouched
-    ps[0].grad += 1                                                               # next batch of the epoch
-    ok &= bool(torch.equal(bucket.reduce(ps)[ps[0]], torch.full((4, 3), 5.0)))
+    # --- a parameter of the frozen layout that gets no gradient in some step contributes zeros (no rank may
+    #     skip or fail a collective: the others would hang) ---
+    ps[1].grad = None
+    ps[0].grad = torch.full_like(ps[0], float(rank + 1))
+    ps[2].grad = torch.zeros_like(ps[2])
+    g2 = sh.reduce_scatter_grads()
+    expect = torch.zeros(sh.shard * world)
+    expect[sh.offsets[0]:sh.offsets[0] + ps[0].numel()] = tot
+    ok &= bool(torch.equal(g2, expect[rank * sh.shard:(rank + 1) * sh.shard]))
+
+    # --- BatchLoader under data parallelism: uneven last batch (9 samples on 2 ranks -> 5 + 4, normaliser 9) and a
+    #     remainder shorter than the world (1 sample on 2 ranks -> replicated, normaliser 2): no empty shard ---
+    from c2dsr_b200.dataloader import BatchLoader, CDSRDataset
+    for n, want_rows, want_glob, want_batch in ((29, (5, 4), 9, 9), (21, (1, 1), 2, 1)):
+        fields = [torch.arange(n * 4).view(n, 4) + 1000 * f for f in range(14)]
+        ds = CDSRDataset.from_fields(fields, "train", 4)
+        batches = list(BatchLoader(ds, 10, rank=rank, world_size=world))
+        ok &= len(batches) == 3 and batches[0][0].shape[0] == 5 and batches[0].global_rows == 10
+        last = batches[-1]
+        ok &= last[0].shape[0] == want_rows[rank] and last.global_rows == want_glob and last.global_batch == want_batch
+        rows = torch.tensor([float(last[0].shape[0])])
+        cdist.allreduce_sum_(rows)
+        ok &= int(rows) == last.global_rows                    # the host-side normaliser equals the all-reduced one
+        # every sample of the epoch is seen exactly once (replicated remainder: once per rank, weight 1 / world)
+        seen = torch.cat([b[0][:, 0] for b in batches]).float()
+        tot_seen = torch.tensor([seen.numel()], dtype=torch.float32)
+        cdist.allreduce_sum_(tot_seen)
+        ok &= int(tot_seen) == n + (want_glob - want_batch)
 
     # --- global normalisers: sum of per-rank valid counts ---
     c = torch.tensor([3.0 + rank, 7.0, 16.0])

@@ -84,7 +84,7 @@ def test_main_entertainment_education_defaults(tmp_path, monkeypatch):
     from c2dsr_b200.main import main
     na, nb = 400, 1500
     raw = tmp_path / "data" / "raw" / "Entertainment-Education"
-    for mode, n, seed in (("train", 1500, 1), ("val", 200, 2), ("test", 200, 3)):
+    for mode, n, seed in (("train", 1500, 1), ("val", 2200, 2), ("test", 200, 3)):
         seqs = synth.make_sequences(n, na, nb, len_max=29, seed=seed, lengths="full")
         synth.write_raw(str(raw / f"{mode}_new.txt"), seqs)
     synth.write_item_lists(str(raw), na, nb)
@@ -93,6 +93,28 @@ def test_main_entertainment_education_defaults(tmp_path, monkeypatch):
     best, res = main(["--data", "ee", "--cuda", "0", "--use_raw", "--n_epoch", "2", "--n_neg_sample", "99"])
     assert len(res) == 13 and all(np.isfinite(res))
     assert 0.0 <= res[1] <= 1.0 and os.listdir(tmp_path / "log")
+    # the model main.py trained, evaluated on the same validation pickles by the CUDA path and by the oracle:
+    # 999-negative-style list ranking (here 99), ranks equal up to near-ties, metrics within 1e-3 (> 1 000 per domain)
+    from c2dsr_b200.metrics import cal_metrics
+    tr = main.last_trainer
+    hp = {k: v for k, v in vars(tr.args).items() if isinstance(v, (int, float, bool, str))}
+    state = {k: v.detach().cpu().clone() for k, v in tr.model.state_dict().items()}
+    otr = oracle.OracleTrainer(state, tr.adj_share.cpu().coalesce(), tr.adj_specific.cpu().coalesce(), hp)
+    tr.model.eval()
+    ra, rb, oa, ob = [], [], [], []
+    with torch.no_grad():
+        tr.model.convolve_graph()
+        otr.convolve_graph()
+        for batch in tr.valloader:
+            a, b = tr.evaluate_batch(batch)
+            ra += a; rb += b
+            a, b = otr.evaluate_batch(tuple(x.cpu() for x in batch))
+            oa += a; ob += b
+    assert len(ra) == len(oa) and len(rb) == len(ob) and min(len(ra), len(rb)) >= 1000
+    diff = np.abs(np.asarray(ra + rb) - np.asarray(oa + ob))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (int(diff.max()), float((diff > 0).mean()))
+    for got, ref in ((ra, oa), (rb, ob)):
+        assert np.abs(np.asarray(cal_metrics(got)) - np.asarray(cal_metrics(ref))).max() <= 1e-3
 
 
 def test_million_item_style_sharded_eval():
