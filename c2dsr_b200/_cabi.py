@@ -56,6 +56,9 @@ _PROTOS = {
     "c2dsr_encoder_select_workspace_bytes": (i64, [i64, i32, i32, i32]),
     "c2dsr_encoder_fwd_select": (i32, [vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32, vp, vp, i64,
                                        vp]),
+    "c2dsr_encoder_padkeys_workspace_bytes": (i64, [i64, i32, i32]),
+    "c2dsr_encoder_fwd_padkeys": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32, vp, vp,
+                                        i64, vp]),
     "c2dsr_encoder_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32] + _DROP
                           + [vp, vp, vp, i64, vp]),
     "c2dsr_attention_fwd": (i32, [vp, vp, i64, i32, i32, i32, i64] + _DROP + [vp, vp, vp]),
@@ -78,8 +81,10 @@ _PROTOS = {
     "c2dsr_rank_from_scores": (i32, [vp, i64, vp, vp, vp, i64, i64, i64, i64, vp, vp]),
     "c2dsr_split_bf16": (i32, [vp, i64, i32, i64, vp, vp, vp]),
     "c2dsr_score_tc_workspace_bytes": (i64, [i64, i64, i32]),
-    "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp]),
-    "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, i64, vp, i64, vp]),
+    "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, i64, vp]),
+    "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, i64, vp, i64, vp]),
+    "c2dsr_eval_partition": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "c2dsr_eval_ranks": (i32, [vp, vp, vp, vp, i64, vp, vp]),
     "c2dsr_adamw_amsgrad": (i32, [vp, i32, i64, f32, f32, f32, f32, f32, i32, vp]),
     "c2dsr_loss_rows_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                   vp]),

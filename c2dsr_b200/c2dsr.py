@@ -121,6 +121,9 @@ class C2DSR(nn.Module):
         self._seed = int(getattr(args, "seed", 0)) * 1_000_003 + 12345
         self._calls = 0
         self._share_calls = 0           # forward_share() calls since convolve_graph(): each gets its own dropout tag
+        # set by the Trainer once it has checked on the host that every PAD token of the evaluation splits has
+        # position 0: forward_select() may then use the pad-key shortcut (ops.branch_padkeys)
+        self.pad_pos_zero = False
 
     def _apply(self, fn, *a, **k):
         """.to()/.cuda(): the CSR graphs follow the parameters; cached propagations are dropped."""
@@ -204,9 +207,9 @@ class C2DSR(nn.Module):
             if st is not cur:
                 st.wait_stream(cur)
             with torch.cuda.stream(st):
-                outs[i] = ops.branch_select(hi, table.weight, attn.pos_emb.weight, seq, pos, sel,
-                                            float(self.d_latent ** 0.5), self.n_item - 1, attn.n_head, attn.norm_first,
-                                            attn.dense_passes_eval, attn.weights())
+                fn = ops.branch_padkeys if (self.pad_pos_zero and not self.training) else ops.branch_select
+                outs[i] = fn(hi, table.weight, attn.pos_emb.weight, seq, pos, sel, float(self.d_latent ** 0.5),
+                             self.n_item - 1, attn.n_head, attn.norm_first, attn.dense_passes_eval, attn.weights())
         for st in self._side[:2]:
             cur.wait_stream(st)
         return tuple(outs)

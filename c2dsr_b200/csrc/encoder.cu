@@ -691,6 +691,23 @@ __global__ void select_rows_kernel(const float* __restrict__ x, const int64_t* _
     for (int e = lane; e < d; e += 32) out[b * d + e] = src[e];
 }
 
+// Pad-key shortcut (evaluation, see c2dsr_encoder_fwd_padkeys): y[b, :] = attention block output of token sel[b]
+// = y_pad when some key j <= sel[b] is a pad token, else the output-projection bias alone (no allowed key: the
+// attention output is 0).  Warp per sequence.
+__global__ void padkey_rows_kernel(const int64_t* __restrict__ seq, const int64_t* __restrict__ sel, int64_t n_seq,
+                                   int L, int d, int64_t pad, const float* __restrict__ y_pad,
+                                   const float* __restrict__ b_o, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n_seq) return;
+    const int i = (int)sel[b];
+    int has = 0;
+    for (int j = lane; j <= i; j += 32) has |= (seq[b * L + j] == pad) ? 1 : 0;
+    has = __any_sync(0xffffffffu, has);
+    const float* src = has ? y_pad : b_o;
+    for (int e = lane; e < d; e += 32) y[b * d + e] = src[e];
+}
+
 static int seq_smem_bytes(const AttnShape& sh, bool bwd) {
     return ((bwd ? 4 : 3) * sh.L * sh.dh + (bwd ? 2 : 1) * sh.L * (sh.L + 1) + 2 * sh.L + 8) * 4;
 }
@@ -963,6 +980,75 @@ int c2dsr_encoder_fwd_select(const c2dsr_layer_weights* layers, int n_layers, co
     }
     RUN(launch_add_ln(last, nullptr, lnf_w, lnf_b, nullptr, out, nullptr, n_seq, d, 1, eps, none, st));
     return check_launch("encoder_fwd_select");
+}
+
+int64_t c2dsr_encoder_padkeys_workspace_bytes(int64_t n_seq, int d, int dense_passes) {
+    return (6 * n_seq + 8) * (int64_t)d * 4 + kGemmWsBytes + (dense_passes ? dense_tc_bytes(n_seq, d) : 0) + 1024;
+}
+
+int c2dsr_encoder_fwd_padkeys(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                              const float* x_sel, const float* x_pad, const int64_t* seq, const int64_t* sel,
+                              int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first,
+                              int dense_passes, float eps, float* out, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+    if (n_seq <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(n_layers == 1, "the pad-key forward covers one encoder layer (use c2dsr_encoder_fwd otherwise)");
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
+    C2DSR_REQUIRE(n_head > 0 && d % n_head == 0, "d must be divisible by n_head");
+    C2DSR_REQUIRE(dense_passes == 0 || dense_passes == 1 || dense_passes == 3, "dense_passes must be 0, 1 or 3");
+    if (workspace_bytes < c2dsr_encoder_padkeys_workspace_bytes(n_seq, d, dense_passes)) {
+        set_error("encoder_fwd_padkeys: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Bd = n_seq * d;
+    float* y = (float*)workspace;               // [n_seq, d] each
+    float* x1 = y + Bd;
+    float* t1 = x1 + Bd;
+    float* t2 = t1 + Bd;
+    float* pad_in = t2 + 3 * Bd;                // pad token: LayerNorm1(x_pad) (pre-norm), qkv [3d], y_pad [d]
+    float* pad_qkv = pad_in + d;
+    float* pad_y = pad_qkv + 3 * d;
+    void* gws = pad_y + 3 * d;
+    void* tws = (char*)gws + kGemmWsBytes;
+    const int64_t tws_bytes = dense_passes ? dense_tc_bytes(n_seq, d) : 0;
+    const Dropout none = make_dropout(0.f, 0, 0);
+    const c2dsr_layer_weights& w = layers[0];
+    // the pad token (one row): value projection and output projection, exact fp32
+    const float* attn_in = x_pad;
+    if (norm_first) {
+        RUN(launch_add_ln(x_pad, nullptr, w.ln1_w, w.ln1_b, nullptr, pad_in, nullptr, 1, d, 1, eps, none, st));
+        attn_in = pad_in;
+    }
+    RUN(dense(0, nullptr, 0, 0, 1, 1, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, pad_qkv, 3 * d, w.in_proj_b, 0, none,
+              gws, kGemmWsBytes, st));
+    RUN(dense(0, nullptr, 0, 0, 1, 1, d, d, 1.f, pad_qkv + 2 * d, d, w.out_proj_w, d, 0.f, pad_y, d, w.out_proj_b, 0, none,
+              gws, kGemmWsBytes, st));
+    padkey_rows_kernel<<<(unsigned)ceil_div(n_seq, 8), 256, 0, st>>>(seq, sel, n_seq, L, d, pad_idx, pad_y, w.out_proj_b,
+                                                                    y);
+    note_launches(1);
+    // from here on exactly c2dsr_encoder_fwd_select: n_seq rows
+    const float* ffn_in;
+    if (norm_first) {
+        RUN(launch_add_ln(x_sel, y, nullptr, nullptr, nullptr, x1, nullptr, n_seq, d, 0, eps, none, st));
+        RUN(launch_add_ln(x1, nullptr, w.ln2_w, w.ln2_b, nullptr, t1, nullptr, n_seq, d, 1, eps, none, st));
+        ffn_in = t1;
+    } else {
+        RUN(launch_add_ln(x_sel, y, w.ln1_w, w.ln1_b, nullptr, x1, nullptr, n_seq, d, 1, eps, none, st));
+        ffn_in = x1;
+    }
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, n_seq, d, d, 1.f, ffn_in, d, w.lin1_w, d, 0.f, t2, d, w.lin1_b, 1, none, gws,
+              kGemmWsBytes, st));
+    RUN(dense(dense_passes, tws, tws_bytes, 0, 1, n_seq, d, d, 1.f, t2, d, w.lin2_w, d, 0.f, y, d, w.lin2_b, 0, none, gws,
+              kGemmWsBytes, st));
+    float* last = t1;
+    if (norm_first) {
+        RUN(launch_add_ln(x1, y, nullptr, nullptr, nullptr, last, nullptr, n_seq, d, 0, eps, none, st));
+    } else {
+        RUN(launch_add_ln(x1, y, w.ln2_w, w.ln2_b, nullptr, last, nullptr, n_seq, d, 1, eps, none, st));
+    }
+    RUN(launch_add_ln(last, nullptr, lnf_w, lnf_b, nullptr, out, nullptr, n_seq, d, 1, eps, none, st));
+    return check_launch("encoder_fwd_padkeys");
 }
 
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers, const c2dsr_layer_grads* grads, int n_layers,

@@ -171,6 +171,71 @@ struct DiagEpilogue {       // BN == BM: element (row, row) of tile (b, b)
 
 constexpr int kBN = 128, kStages = 3;
 
+// ---- evaluation batch on the device: stable partition of the queries by domain -------------------------------
+// one block: slot[i] = number of earlier queries of the same domain (block-wide exclusive scan over chunks of 1024)
+__global__ void __launch_bounds__(1024) eval_slots_kernel(const int64_t* __restrict__ dom, int64_t B,
+                                                          int32_t* __restrict__ slot, int32_t* __restrict__ n_ab) {
+    __shared__ int warp_tot[32];
+    __shared__ int base_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_b = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < B; c0 += 1024) {
+        const int64_t i = c0 + threadIdx.x;
+        const int is_b = (i < B && dom[i] != 0) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_b);
+        const int before = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += warp_tot[w];
+        const int nb_before = base_b + wbase + before;              // B-domain queries among [0, i)
+        if (i < B) slot[i] = is_b ? nb_before : (int)(i - nb_before);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_tot[w];
+            base_b += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        n_ab[0] = (int)(B - base_b);
+        n_ab[1] = base_b;
+    }
+}
+
+// block per query: its row goes to slot[i] of its domain's buffer as bf16 hi / lo
+__global__ void eval_scatter_kernel(const float* __restrict__ q, const int64_t* __restrict__ dom,
+                                    const int64_t* __restrict__ gt, const int32_t* __restrict__ slot, int d,
+                                    uint16_t* __restrict__ QA_hi, uint16_t* __restrict__ QA_lo,
+                                    uint16_t* __restrict__ QB_hi, uint16_t* __restrict__ QB_lo,
+                                    int64_t* __restrict__ gtA, int64_t* __restrict__ gtB) {
+    const int64_t i = blockIdx.x;
+    const bool is_b = dom[i] != 0;
+    const int64_t r = slot[i];
+    uint16_t* hi = (is_b ? QB_hi : QA_hi) + r * d;
+    uint16_t* lo = is_b ? QB_lo : QA_lo;
+    if (lo) lo += r * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        uint16_t h, l;
+        split2(q[i * d + c], h, l);
+        hi[c] = h;
+        if (lo) lo[c] = l;
+    }
+    if (threadIdx.x == 0) (is_b ? gtB : gtA)[r] = gt[i];
+}
+
+__global__ void eval_ranks_kernel(const int32_t* __restrict__ cA, const int32_t* __restrict__ cB,
+                                  const int32_t* __restrict__ slot, const int64_t* __restrict__ dom, int64_t B,
+                                  int32_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const bool is_b = dom[i] != 0;
+    out[i] = 1 + (is_b ? cB : cA)[slot[i]];
+    out[B + i] = is_b ? 1 : 0;
+}
+
 }  // namespace c2dsr
 
 using namespace c2dsr;
@@ -188,6 +253,26 @@ int c2dsr_split_bf16(const float* X, int64_t rows, int d, int64_t ld_out, uint16
     return split_rows(X, rows, d, ld_out, hi, lo, (cudaStream_t)stream);
 }
 
+int c2dsr_eval_partition(const float* q, const int64_t* dom, const int64_t* gt, int64_t B, int d, uint16_t* QA_hi,
+                         uint16_t* QA_lo, uint16_t* QB_hi, uint16_t* QB_lo, int64_t* gtA, int64_t* gtB, int32_t* slot,
+                         int32_t* n_ab, void* stream) {
+    if (B <= 0) return C2DSR_OK;
+    RUN(c2dsr_device_check());
+    cudaStream_t st = (cudaStream_t)stream;
+    eval_slots_kernel<<<1, 1024, 0, st>>>(dom, B, slot, n_ab);
+    eval_scatter_kernel<<<(unsigned)B, 128, 0, st>>>(q, dom, gt, slot, d, QA_hi, QA_lo, QB_hi, QB_lo, gtA, gtB);
+    note_launches(2);
+    return check_launch("eval_partition");
+}
+
+int c2dsr_eval_ranks(const int32_t* countsA, const int32_t* countsB, const int32_t* slot, const int64_t* dom, int64_t B,
+                     int32_t* out, void* stream) {
+    if (B <= 0) return C2DSR_OK;
+    eval_ranks_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(countsA, countsB, slot, dom, B, out);
+    note_launches(1);
+    return check_launch("eval_ranks");
+}
+
 int64_t c2dsr_score_tc_workspace_bytes(int64_t n_q, int64_t n_shard, int d) {
     (void)n_shard;
     const int64_t rows = align_up(n_q > 0 ? n_q : 1, tc::BM);
@@ -196,7 +281,8 @@ int64_t c2dsr_score_tc_workspace_bytes(int64_t n_q, int64_t n_shard, int d) {
 
 int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                           const float* bias, const int64_t* gt, int64_t n_q, int64_t n0, int64_t n1, int d,
-                          int passes, float* s_gt, void* workspace, int64_t workspace_bytes, void* stream) {
+                          int passes, const int* n_q_limit, float* s_gt, void* workspace, int64_t workspace_bytes,
+                          void* stream) {
     if (n_q <= 0) return C2DSR_OK;
     RUN(c2dsr_device_check());
     C2DSR_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
@@ -215,7 +301,7 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
     note_launches(1);
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
-    tc::Problem pb{n_q, n_q, d, passes, 1, 1};
+    tc::Problem pb{n_q, n_q, d, passes, 1, 1, n_q_limit};
     DiagEpilogue epi{bias_gt, s_gt, n_q};
     if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, st);
     return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, st);
@@ -223,8 +309,8 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
 
 int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                          const float* bias, const float* s_gt, const int64_t* gt, int64_t n_q, int64_t n0,
-                         int64_t n1, int d, int passes, int32_t* counts, float* S_debug, int64_t lds,
-                         void* workspace, int64_t workspace_bytes, void* stream) {
+                         int64_t n1, int d, int passes, const int* n_q_limit, int32_t* counts, float* S_debug,
+                         int64_t lds, void* workspace, int64_t workspace_bytes, void* stream) {
     (void)workspace; (void)workspace_bytes;
     if (n_q <= 0 || n1 <= n0) return C2DSR_OK;
     RUN(c2dsr_device_check());
@@ -233,7 +319,7 @@ int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint1
     const int64_t n = n1 - n0;
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, W_hi, W_lo, n, d, d, passes));
-    tc::Problem pb{n_q, n, d, passes, 0, 1};
+    tc::Problem pb{n_q, n, d, passes, 0, 1, n_q_limit};
     CountEpilogue epi{bias, s_gt, gt, counts, S_debug, lds, n_q, n, n0, 0.f, 0, 0};
     // the queries' row block stays resident in shared memory when it fits (d <= 256); same MMA sequence either way
     if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, (cudaStream_t)stream);

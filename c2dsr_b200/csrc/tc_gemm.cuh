@@ -23,6 +23,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace c2dsr {
 namespace tc {
@@ -78,6 +79,27 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         : "memory");
 }
 
+// elect.sync-predicated forms for a producer warp that runs its loop with all lanes (see umma_bf16_elect: a
+// `lane == 0` branch anywhere in the role code makes ptxas treat the MMA issuer's counters as per-thread values)
+__device__ __forceinline__ void mbar_arrive_expect_tx_elect(uint64_t* bar, uint32_t bytes) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(bytes)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_elect(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t"
+        "}" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+
 // ---- tensor memory ----
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -99,6 +121,83 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The MMA-issuing warp runs its loops with ALL lanes (warp-uniform control flow) and predicates only the instruction
+// itself on elect.sync: every operand then comes from provably uniform values (shared-memory base, kernel
+// parameters, block index, a __shfl_sync broadcast of the TMEM base) and stays in uniform registers.  Issuing from a
+// single lane (`if (lane == 0)`) made the compiler wrap each UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop
+// (~20 SASS instructions, > 100 cycles per MMA): the N = 128 kernels were issue-bound at ~55 % tensor-pipe activity
+// (scratch/mma_issue_bench.cu: 64.0 cycles per 128x128x16 MMA = nominal with this form).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The shared-memory descriptor as two 32-bit halves: only the low word depends on the address (start address >> 4 in
+// bits 0-13, leading byte offset >> 4 in bits 16-29); the high word (stride byte offset 1024 >> 4, descriptor
+// version 1, SWIZZLE_128B) is the same constant for every operand tile of these kernels.
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, bool mn_major) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | ((uint32_t)(mn_major ? (BK * 128) >> 4 : 1) << 16);
+}
+__device__ __forceinline__ uint32_t uniform32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
+__device__ __forceinline__ void umma_lo_elect(uint32_t tmem_d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b32 hi;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b32 hi, %5;\n\t"
+        "mov.b64 da, {%1, hi};\n\t"
+        "mov.b64 db, {%2, hi};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo32), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(kDescHi)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo_elect(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo32, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b32 hi;\n\t"
+        ".reg .b64 db;\n\t"
+        "mov.b32 hi, %5;\n\t"
+        "mov.b64 db, {%2, hi};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo32), "r"(idesc), "r"(accumulate), "n"(kDescHi)
+        : "memory");
+}
+// A from tensor memory (bf16 pairs packed along K, one row per lane), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                   uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
         : "memory");
 }
 // mbarrier arrives once every previously issued MMA of this thread has completed
@@ -159,6 +258,9 @@ struct Problem {
     int passes;         // 3 = hi/lo split, 1 = hi only
     int diag_only;      // 1: only tiles with m_blk == n_blk (target-score pass, BN == BM)
     int k_splits;       // >= 1: K is cut into this many slabs; the epilogue receives the slab index
+    const int* m_limit; // optional device-resident row count: only the first min(M, *m_limit) rows of A are computed
+                        // (M stays the capacity the tensor maps and the launch were sized for; lets a captured
+                        // launch follow a row count that is only known on the device)
 };
 
 template <int BN, int STAGES, bool ARES>
@@ -172,6 +274,49 @@ struct SmemLayout {
     static constexpr int BARRIER_OFF = RING_OFF + STAGES * STAGE;
     static constexpr int TOTAL = BARRIER_OFF + 256 + 1024;   // barriers + tmem pointer + alignment slack
 };
+
+// Compile-time dispatch of a small runtime index: f(std::integral_constant<int, v>).  The MMA issuer uses it to turn
+// the ring stage, the accumulator stage and (resident A) the k-block into constants, so that every descriptor is
+// "shared-memory base + constant": values that live in uniform registers from birth, with no per-MMA R2UR traffic.
+template <int N, class F>
+__device__ __forceinline__ void dispatch_index(int v, F&& f) {
+    if constexpr (N <= 1) {
+        f(std::integral_constant<int, 0>{});
+    } else {
+        if (v == N - 1) f(std::integral_constant<int, N - 1>{});
+        else dispatch_index<N - 1>(v, f);
+    }
+}
+
+// the 4 (passes = 1) or 12 (passes = 3) MMAs of one 64-wide k-block
+template <int BN, int STAGES, bool ARES, bool A_MN, bool B_MN, int STAGE, int ACC, int KB>
+__device__ __forceinline__ void issue_kblock(uint32_t smem_base, uint32_t tmem_base, bool split, uint32_t accum0) {
+    using L = SmemLayout<BN, STAGES, ARES>;
+    constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
+    constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
+    constexpr uint32_t st_off = (uint32_t)(L::RING_OFF + STAGE * L::STAGE);
+    constexpr uint32_t a_off = ARES ? (uint32_t)(KB * 2 * L::A_TILE) : st_off;
+    constexpr uint32_t b_off = st_off + (uint32_t)L::B_OFF;
+    constexpr uint32_t lbo_a = (uint32_t)(A_MN ? (BK * 128) >> 4 : 1) << 16, lbo_b = (uint32_t)(B_MN ? (BK * 128) >> 4 : 1) << 16;
+    // (smem_base is 1024-byte aligned and below 256 KB: the address field of base + offset is the sum of the fields)
+    const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
+    const uint32_t a_hi = (base16 + (a_off >> 4)) | lbo_a, a_lo = a_hi + (uint32_t)(L::A_TILE >> 4);
+    const uint32_t b_hi = (base16 + (b_off >> 4)) | lbo_b, b_lo = b_hi + (uint32_t)(L::B_TILE >> 4);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(ACC * BN);
+    if (split) {          // small cross terms first, then the leading product
+        umma_lo_elect(d_tmem, a_lo, b_hi, idesc, accum0);
+#pragma unroll
+        for (int k = 1; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, 1u);
+    } else {
+        umma_lo_elect(d_tmem, a_hi, b_hi, idesc, accum0);
+#pragma unroll
+        for (int k = 1; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, 1u);
+    }
+}
 
 // Epilogue functor contract (one instance per epilogue thread; the thread owns A row `row`):
 //   void tile_begin(int64_t m_blk, int64_t n_blk, int64_t row, int k_slab, int part);
@@ -189,22 +334,21 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         if (A_MN) {
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g)
-                tma_load_2d(map, bar, dst + g * MN_GROUP_BYTES, (int)(m_blk * BM) + 64 * g, kb * BK);
+                tma_load_2d_elect(map, bar, dst + g * MN_GROUP_BYTES, (int)(m_blk * BM) + 64 * g, kb * BK);
         } else {
-            tma_load_2d(map, bar, dst, kb * BK, (int)(m_blk * BM));
+            tma_load_2d_elect(map, bar, dst, kb * BK, (int)(m_blk * BM));
         }
     };
     auto load_b = [&](const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int kb, int64_t n_blk) {
         if (B_MN) {
 #pragma unroll
             for (int g = 0; g < BN / 64; ++g)
-                tma_load_2d(map, bar, dst + g * MN_GROUP_BYTES, (int)(n_blk * BN) + 64 * g, kb * BK);
+                tma_load_2d_elect(map, bar, dst + g * MN_GROUP_BYTES, (int)(n_blk * BN) + 64 * g, kb * BK);
         } else {
-            tma_load_2d(map, bar, dst, kb * BK, (int)(n_blk * BN));
+            tma_load_2d_elect(map, bar, dst, kb * BK, (int)(n_blk * BN));
         }
     };
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];       // (1024-byte aligned: what the 128B swizzle atoms need)
     uint8_t* ring = smem + L::RING_OFF;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BARRIER_OFF);
     uint64_t* empty = full + STAGES;
@@ -214,8 +358,13 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
     uint64_t* a_empty = a_full + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m_blocks = (pb.M + BM - 1) / BM, n_blocks = (pb.N + BN - 1) / BN;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    int64_t M_eff = pb.M;
+    if (pb.m_limit) {
+        const int64_t lim = *pb.m_limit;
+        M_eff = lim < M_eff ? (lim > 0 ? lim : 0) : M_eff;
+    }
+    const int64_t m_blocks = (M_eff + BM - 1) / BM, n_blocks = (pb.N + BN - 1) / BN;
     const int ks = pb.k_splits > 1 ? pb.k_splits : 1;
     const int64_t n_tiles = pb.diag_only ? m_blocks : m_blocks * n_blocks * ks;
     const int n_kb_total = (pb.K + BK - 1) / BK;
@@ -268,7 +417,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
     // tile t -> (m_blk, n_blk, k slab); slabs of one output tile are consecutive
     auto tile_coords = [&](int64_t t, int64_t& m_blk, int64_t& n_blk, int& slab) {
@@ -287,8 +436,11 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         kb1 = kb0 + kb_per_slab < n_kb_total ? kb0 + kb_per_slab : n_kb_total;
     };
 
-    if (warp == 0 && lane == 0) {
-        // ---------------- TMA producer ----------------
+    // (role branches are on the warp index only -- provably warp-uniform -- so that ptxas keeps the issuer's loop
+    //  counters and descriptors in uniform registers; the lane test of the producer is nested inside its branch)
+    if (warp == 0) {
+        // ---------------- TMA producer: all lanes run the loop, elect.sync issues ----------------
+        {
         int stage = 0;
         uint32_t phase = 0, a_phase = 0;
         int64_t cur_m = -1;
@@ -299,7 +451,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             kb_range(slab, kb0, kb1);
             if (ARES && m_blk != cur_m) {
                 mbar_wait(a_empty, a_phase ^ 1);              // MMAs of the previous row block are done
-                mbar_arrive_expect_tx(a_full, (uint32_t)n_kb_total * (uint32_t)L::A_TILE * (split ? 2u : 1u));
+                mbar_arrive_expect_tx_elect(a_full, (uint32_t)n_kb_total * (uint32_t)L::A_TILE * (split ? 2u : 1u));
                 for (int kb = 0; kb < n_kb_total; ++kb) {
                     load_a(&maps.a_hi, a_full, smem + kb * 2 * L::A_TILE, kb, m_blk);
                     if (split) load_a(&maps.a_lo, a_full, smem + kb * 2 * L::A_TILE + L::A_TILE, kb, m_blk);
@@ -310,7 +462,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = ring + stage * L::STAGE;
-                mbar_arrive_expect_tx(&full[stage], stage_bytes);
+                mbar_arrive_expect_tx_elect(&full[stage], stage_bytes);
                 if (!ARES) {
                     load_a(&maps.a_hi, &full[stage], st, kb, m_blk);
                     if (split) load_a(&maps.a_lo, &full[stage], st + L::A_TILE, kb, m_blk);
@@ -323,10 +475,10 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---------------- MMA issuer ----------------
-        constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
-        constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: the whole warp runs the loop, elect.sync picks the issuing lane ----------------
+        const uint32_t smem_base = smem_u32(smem);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0, a_phase = 0;
         int64_t cur_m = -1;
@@ -336,44 +488,46 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             tile_coords(t, m_blk, n_blk, slab);
             kb_range(slab, kb0, kb1);
             if (ARES && m_blk != cur_m) {
-                if (cur_m >= 0) umma_commit(a_empty);          // previous row block no longer needed
+                if (cur_m >= 0) umma_commit_elect(a_empty);          // previous row block no longer needed
                 mbar_wait(a_full, a_phase);
                 a_phase ^= 1;
                 cur_m = m_blk;
             }
             mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
             tcgen05_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tcgen05_fence_after();
-                const uint32_t st = smem_u32(ring + stage * L::STAGE);
-                const uint32_t a_base = ARES ? smem_u32(smem + kb * 2 * L::A_TILE) : st;
-                const uint64_t a_hi = make_smem_desc(a_base, A_MN), a_lo = make_smem_desc(a_base + L::A_TILE, A_MN);
-                const uint64_t b_hi = make_smem_desc(st + L::B_OFF, B_MN);
-                const uint64_t b_lo = make_smem_desc(st + L::B_OFF + L::B_TILE, B_MN);
+                // descriptor low words from the (warp-uniform) stage / k-block counters: uniform-datapath arithmetic
+                const uint32_t st = smem_base + (uint32_t)(L::RING_OFF + stage * L::STAGE);
+                const uint32_t a_base = ARES ? smem_base + (uint32_t)(kb * 2 * L::A_TILE) : st;
+                const uint32_t a_hi = desc_lo(a_base, A_MN), a_lo = a_hi + (uint32_t)(L::A_TILE >> 4);
+                const uint32_t b_hi = desc_lo(st + L::B_OFF, B_MN), b_lo = b_hi + (uint32_t)(L::B_TILE >> 4);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
+                constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
                 uint32_t accum = kb > kb0 ? 1u : 0u;
                 if (split) {      // small cross terms first, then the leading product
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, accum);
+                        umma_lo_elect(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, accum);
                         accum = 1u;
                     }
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) umma_bf16(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
                 }
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_bf16(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, accum);
+                    umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, accum);
                     accum = 1u;
                 }
-                umma_commit(&empty[stage]);          // smem stage is free once these MMAs retire
+                umma_commit_elect(&empty[stage]);          // smem stage is free once these MMAs retire
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;
                 }
             }
-            umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+            umma_commit_elect(&tmem_full[acc]);            // accumulator complete -> epilogue
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;

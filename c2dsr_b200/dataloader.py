@@ -210,6 +210,9 @@ class CDSRDataset(torch.utils.data.Dataset):
             raise IndexError(f"{self.mode} split: position {hi_pos} >= len_max = {self.len_max} "
                              "(a sequence longer than len_max items; the reference raises IndexError here too)")
         self.n_fully_masked = int((self.fields[0][:, 0] != n_item - 1).sum()) if self.length else 0
+        # every PAD token carries position 0 (dataloader.py:137-143 of the reference pads both with the same
+        # offsets): what the evaluation's pad-key shortcut relies on
+        self.pad_pos_zero = all(bool((p[s == n_item - 1] == 0).all()) for s, p in zip(seqs, poss))
         return self.n_fully_masked
 
     def to(self, device, pin: bool = False):

@@ -232,6 +232,33 @@ def branch_select(hi, E, P, seq, pos, sel, scale: float, pad_idx: int, n_head: i
     return out
 
 
+@torch.no_grad()
+def branch_padkeys(hi, E, P, seq, pos, sel, scale: float, pad_idx: int, n_head: int, norm_first: bool,
+                   dense_passes: int, weights):
+    """Evaluation form of one branch when every PAD token has position 0 (the preprocessor's invariant, checked by
+    CDSRDataset.check_bounds): h[b, sel[b], :] without projecting or attending over the B * L tokens at all -- the
+    reference's inverted key-padding mask lets a query see PAD keys only, and those are all the same
+    row.  One gather of B + 1 tokens (the selected ones and one PAD token), then c2dsr_encoder_fwd_padkeys."""
+    hi, E, P = _f(hi), _f(E), _f(P)
+    seq, pos, sel = seq.contiguous(), pos.contiguous(), sel.contiguous()
+    w = [_f(t) for t in weights]
+    n_seq, L = seq.shape
+    d = E.shape[1]
+    ids = torch.empty(n_seq + 1, dtype=I64, device=seq.device)
+    ps = torch.zeros(n_seq + 1, dtype=I64, device=seq.device)
+    torch.gather(seq, 1, sel.view(-1, 1), out=ids[:n_seq].view(-1, 1))
+    torch.gather(pos, 1, sel.view(-1, 1), out=ps[:n_seq].view(-1, 1))
+    ids[n_seq:].fill_(pad_idx)                                    # (a fill kernel: no host copy)
+    x = _gather_forward(hi, E, P, ids, ps, scale, 0.0, 0, 0)      # [n_seq + 1, d]; the last row is the PAD token
+    out = torch.empty(n_seq, d, device=E.device, dtype=F32)
+    ws = workspace.get(query("c2dsr_encoder_padkeys_workspace_bytes", n_seq, d, dense_passes), E.device)
+    table = _layer_table(w, 1)
+    call("c2dsr_encoder_fwd_padkeys", C.addressof(table), 1, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(x[n_seq:]), ptr(seq, I64),
+         ptr(sel, I64), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, ptr(out), ptr(ws),
+         ws.numel(), stream())
+    return out
+
+
 class BranchSetFn(torch.autograd.Function):
     """Several independent branches (K1 gather + K3 encoder each) as ONE autograd node that forks them
     onto CUDA streams and joins before returning, in forward and in backward.  One branch alone is too
@@ -601,18 +628,22 @@ def rank_from_scores(S, s_gt, gt, neg: Optional[torch.Tensor], n0: int, n1: int,
 BF16 = torch.bfloat16
 
 
-def split_bf16(X: torch.Tensor, want_lo: bool = True):
-    """x = hi + lo with hi = bf16(x), lo = bf16(x - hi): operands of the 3-pass (fp32-grade) MMA."""
+def split_bf16(X: torch.Tensor, want_lo: bool = True, out=None):
+    """x = hi + lo with hi = bf16(x), lo = bf16(x - hi): operands of the 3-pass (fp32-grade) MMA.  ``out`` =
+    an earlier (hi, lo) result to overwrite in place."""
     X = _f(X)
     rows, d = X.shape
-    hi = torch.empty(rows, d, device=X.device, dtype=BF16)
-    lo = torch.empty(rows, d, device=X.device, dtype=BF16) if want_lo else None
+    if out is not None:
+        hi, lo = out
+    else:
+        hi = torch.empty(rows, d, device=X.device, dtype=BF16)
+        lo = torch.empty(rows, d, device=X.device, dtype=BF16) if want_lo else None
     call("c2dsr_split_bf16", ptr(X), rows, d, d, ptr(hi), ptr(lo), stream())
     return hi, lo
 
 
 def score_rank_tc(Q, W_split, bias, gt, n0: int, n1: int, passes: int = 3, neg=None, s_gt=None,
-                  counts=None, want_scores: bool = False, reduce_s_gt=None):
+                  counts=None, want_scores: bool = False, reduce_s_gt=None, n_q_limit=None):
     """Full-catalogue partial rank counts of queries Q against the catalogue shard [n0, n1).
 
     W_split = split_bf16(W[n0:n1]) (cached by the caller while the weights do not change).
@@ -631,7 +662,7 @@ def score_rank_tc(Q, W_split, bias, gt, n0: int, n1: int, passes: int = 3, neg=N
     if s_gt is None:
         s_gt = torch.zeros(n_q, device=dev, dtype=F32)
         call("c2dsr_score_target_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(gt, I64), n_q, n0, n1,
-             d, passes, ptr(s_gt), ptr(ws), ws.numel(), stream())
+             d, passes, ptr(n_q_limit), ptr(s_gt), ptr(ws), ws.numel(), stream())
         if reduce_s_gt is not None:
             reduce_s_gt(s_gt)
     if counts is None:
@@ -639,5 +670,5 @@ def score_rank_tc(Q, W_split, bias, gt, n0: int, n1: int, passes: int = 3, neg=N
     lds = (n + 3) // 4 * 4
     S = torch.empty(n_q, lds, device=dev, dtype=F32) if want_scores else None
     call("c2dsr_score_count_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(s_gt), ptr(gt, I64), n_q,
-         n0, n1, d, passes, ptr(counts, I32), ptr(S), lds, None, 0, stream())
+         n0, n1, d, passes, ptr(n_q_limit), ptr(counts, I32), ptr(S), lds, None, 0, stream())
     return counts, s_gt, S

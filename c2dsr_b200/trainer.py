@@ -60,6 +60,9 @@ class Trainer(object):
                 if n_masked and noter is not None and hasattr(noter, "log_msg"):
                     noter.log_msg(f"\t| note  | {ld.dataset.mode}: {n_masked} sequences start with a real item; their "
                                   "leading query rows have no allowed key (reference: NaN-prone, here: 0)")
+        evals = [ld for ld in (self.valloader, self.testloader) if ld is not None and hasattr(ld.dataset, "pad_pos_zero")]
+        self.model.pad_pos_zero = bool(getattr(args, "eval_pad_shortcut", True)) and len(evals) > 0 and \
+            all(ld.dataset.pad_pos_zero for ld in evals)
         if getattr(args, "data_on_device", True):
             for ld in (self.trainloader, self.valloader, self.testloader):
                 if ld is not None and hasattr(ld.dataset, "to"):
@@ -94,14 +97,25 @@ class Trainer(object):
         self._graphs, self._warm, self._caps = {}, {}, None
         self._eval_graph, self._eval_seen = None, None
 
+    def enable_pad_shortcut(self, eval_batches) -> bool:
+        """For evaluation batches that do not come from this trainer's loaders (benchmarks, tests): check on the host
+        that every PAD token has position 0 and, if so, let forward_select() use the pad-key shortcut."""
+        pad = self.args.n_item - 1
+        ok = all(bool((b[3 + k].cpu()[b[k].cpu() == pad] == 0).all()) for b in eval_batches for k in range(3))
+        self.model.pad_pos_zero = ok and bool(getattr(self.args, "eval_pad_shortcut", True))
+        return self.model.pad_pos_zero
+
     def _split_cache(self, weight, n0, n1):
         """bf16 (hi, lo) split of a classifier shard, refreshed whenever the weights change."""
         key = (weight.data_ptr(), n0, n1)
         ver = (weight._version, getattr(self.optimizer, "n_steps", 0))   # raw-pointer updates do not bump _version
         hit = self._wsplit.get(key)
-        if hit is None or hit[0] != ver:
-            hit = (ver, ops.split_bf16(weight.detach()[n0:n1], self.tc_passes == 3))
+        if hit is None:
+            hit = [ver, ops.split_bf16(weight.detach()[n0:n1], self.tc_passes == 3)]
             self._wsplit[key] = hit
+        elif hit[0] != ver:              # refreshed in place: captured evaluation graphs keep reading these buffers
+            ops.split_bf16(weight.detach()[n0:n1], self.tc_passes == 3, out=hit[1])
+            hit[0] = ver
         return hit[1]
 
     # ------------------------------------------------------------------------------------------
@@ -255,7 +269,8 @@ class Trainer(object):
             return self.train_batch(batch)
         nv = self._valid_rows(batch) if self.skip_ignored else None
         # (the infomax normaliser 1 / global rows is baked into the captured launch: part of the key)
-        key = (tuple(batch[0].shape), nv is not None, getattr(batch, "global_rows", None))
+        key = (tuple(batch[0].shape), nv is not None,
+               getattr(batch, "global_rows", None) or batch[0].shape[0] * self.world_size)
         g = self._graphs.get(key)
         if g is None:
             seen = self._warm.setdefault(key, [])
@@ -405,9 +420,87 @@ class Trainer(object):
         cdist.allreduce_sum_(counts)
         return counts + 1
 
+    # ---- full-catalogue evaluation of a batch entirely on the device (one CUDA graph, one host read) ----------
+    def _eval_fused_body(self, f):
+        """f = the first ten evaluation fields on the device (global batch, identical on every rank).  Encoders on
+        this rank's slice of the queries, all-gather of the query vectors, stable partition by domain on the device
+        (c2dsr_eval_partition), per domain the target-score and counting GEMMs over this rank's catalogue shard with
+        the domain's query count read from device memory, sum all-reduces of target scores and counts, ranks."""
+        seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b, xory, gt_last = f
+        Bg, d, dev = seq_share.shape[0], self.d_latent, self.device
+        r0, r1 = cdist.shard_bounds(Bg, self.rank, self.world_size) if self.world_size > 1 else (0, Bg)
+        dom, gt = xory.view(-1).contiguous(), gt_last.view(-1).contiguous()
+        if r1 > r0:
+            q = self._encode_body(tuple(x[r0:r1] for x in (seq_share, seq_a, seq_b, pos, pos_a, pos_b, idx_a, idx_b))
+                                  + (dom[r0:r1] != 0,))
+        else:
+            q = torch.zeros(0, d, device=dev)
+        q = cdist.allgather_rows(q.contiguous(), Bg)
+        split = self.tc_passes == 3
+        cap = -(-Bg // 128) * 128
+        bf = lambda: torch.zeros(cap, d, dtype=torch.bfloat16, device=dev)
+        QA_hi, QB_hi = bf(), bf()
+        QA_lo, QB_lo = (bf(), bf()) if split else (None, None)
+        gts = torch.zeros(2, cap, dtype=torch.int64, device=dev)
+        slot = torch.empty(Bg, dtype=torch.int32, device=dev)
+        n_ab = torch.zeros(2, dtype=torch.int32, device=dev)
+        call("c2dsr_eval_partition", ptr(q), ptr(dom), ptr(gt), Bg, d, ptr(QA_hi), ptr(QA_lo), ptr(QB_hi), ptr(QB_lo),
+             ptr(gts[0]), ptr(gts[1]), ptr(slot), ptr(n_ab), stream())
+        s_gt = torch.zeros(2, cap, dtype=torch.float32, device=dev)
+        counts = torch.zeros(2, cap, dtype=torch.int32, device=dev)
+        jobs = []
+        for k, (cls, Q_hi, Q_lo) in enumerate(((self.model.classifier_a, QA_hi, QA_lo),
+                                               (self.model.classifier_b, QB_hi, QB_lo))):
+            n0, n1 = cdist.shard_bounds(cls.weight.shape[0], self.rank, self.world_size)
+            W_hi, W_lo = self._split_cache(cls.weight, n0, n1)
+            bias = cls.bias.detach()[n0:n1].contiguous()
+            ws = workspace.get(query("c2dsr_score_tc_workspace_bytes", cap, n1 - n0, d), dev)
+            call("c2dsr_score_target_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(gts[k]), cap, n0, n1,
+                 d, self.tc_passes, ptr(n_ab[k:]), ptr(s_gt[k]), ptr(ws), ws.numel(), stream())
+            jobs.append((Q_hi, Q_lo, W_hi, W_lo, bias, n0, n1))
+        cdist.allreduce_sum_(s_gt)                         # the owner shard's score + zeros (exact)
+        for k, (Q_hi, Q_lo, W_hi, W_lo, bias, n0, n1) in enumerate(jobs):
+            call("c2dsr_score_count_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(s_gt[k]), ptr(gts[k]),
+                 cap, n0, n1, d, self.tc_passes, ptr(n_ab[k:]), ptr(counts[k]), None, 0, None, 0, stream())
+        cdist.allreduce_sum_(counts)                       # integer partial counts: order independent, bit-exact
+        out = torch.empty(2, Bg, dtype=torch.int32, device=dev)
+        call("c2dsr_eval_ranks", ptr(counts[0]), ptr(counts[1]), ptr(slot), ptr(dom), Bg, ptr(out), stream())
+        return out
+
+    def _evaluate_fused(self, batch):
+        m = self.model
+        f = tuple(batch[:10])
+        key = (tuple(f[0].shape), m.hi_share.data_ptr(), m.hi_a.data_ptr(), m.hi_b.data_ptr(), self.tc_passes)
+        g = self._eval_graph
+        if not self.use_graph or g is None or g["key"] != key:
+            f_dev = tuple(x.to(self.device, non_blocking=True) for x in f)
+            if not self.use_graph or self._eval_seen != key:       # first batch of a shape / phase: eager
+                self._eval_seen = key
+                out = self._eval_fused_body(f_dev)
+                r = out.cpu().numpy()
+                return r[0][r[1] == 0].tolist(), r[0][r[1] != 0].tolist()
+            static = tuple(x.clone() for x in f_dev)
+            workspace.pinned = True
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            l0 = _cabi.launch_count()
+            with torch.cuda.graph(graph):
+                out = self._eval_fused_body(static)
+            g = self._eval_graph = dict(key=key, graph=graph, static=static, out=out,
+                                        launches=_cabi.launch_count() - l0)
+        for s_, x in zip(g["static"], f):
+            s_.copy_(x, non_blocking=True)
+        g["graph"].replay()
+        _cabi.REPLAYED_LAUNCHES += g["launches"]
+        r = g["out"].cpu().numpy()                          # the batch's one device -> host read
+        return r[0][r[1] == 0].tolist(), r[0][r[1] != 0].tolist()
+
     @torch.no_grad()
     def evaluate_batch(self, batch):
         """trainer.py:162-181 -> (rank_a, rank_b) Python lists in batch order."""
+        if self.full_catalog and self.score_path == "tc" and batch[0].shape[0] > 0 and \
+                self.model.attn_share.n_layers == 1 and self.model.hi_share is not None:
+            return self._evaluate_fused(batch)
         xory_host = batch[8].view(-1).cpu()          # (before anything is enqueued: the device is idle or behind)
         # full-catalogue mode never reads list_neg: leave it on the host
         batch = tuple(x if (i == 10 and self.full_catalog) else x.to(self.device, non_blocking=True)

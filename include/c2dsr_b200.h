@@ -131,6 +131,19 @@ int c2dsr_encoder_fwd_select(const c2dsr_layer_weights* layers_host, int n_layer
                              const float* lnf_b, const float* x, const int64_t* seq, const int64_t* sel, int64_t n_seq,
                              int L, int d, int n_head, int64_t pad_idx, int norm_first, int dense_passes, float eps,
                              float* out, void* workspace, int64_t workspace_bytes, void* stream);
+/* Pad-key shortcut of the single-query forward (evaluation, one encoder layer, no dropout).  Under the reference's
+ * inverted key-padding mask (models/encoders.py:33) a query attends only to PAD tokens at or before it,
+ * and every PAD token of a branch has the same input row x_pad = sqrt(d) (hi[PAD] + E[PAD]) + P[0] (the preprocessor
+ * gives pad tokens position 0; the host checks that once per split).  Identical keys -> uniform soft-max ->
+ * the attention output of any query with at least one allowed key is the value row of x_pad; with none it is 0.
+ * So: x_sel [n_seq, d] = input rows of the selected tokens, x_pad [d]; seq / sel only decide "has an allowed key".
+ * No QKV projection or attention over the n_seq * L tokens is computed at all. */
+int64_t c2dsr_encoder_padkeys_workspace_bytes(int64_t n_seq, int d, int dense_passes);
+int c2dsr_encoder_fwd_padkeys(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
+                              const float* x_sel, const float* x_pad, const int64_t* seq, const int64_t* sel,
+                              int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first,
+                              int dense_passes, float eps, float* out, void* workspace, int64_t workspace_bytes,
+                              void* stream);
 /* Gradients are ACCUMULATED (+=) into `grads` and lnf grads; dx is overwritten. */
 int c2dsr_encoder_bwd(const c2dsr_layer_weights* layers_host, const c2dsr_layer_grads* grads_host, int n_layers,
                       const float* lnf_w, float* d_lnf_w, float* d_lnf_b, const float* d_out, const int64_t* seq,
@@ -231,13 +244,28 @@ int c2dsr_rank_from_scores(const float* S, int64_t lds, const float* s_gt, const
 int c2dsr_split_bf16(const float* X, int64_t rows, int d, int64_t ld_out, uint16_t* hi, uint16_t* lo,
                      void* stream);
 int64_t c2dsr_score_tc_workspace_bytes(int64_t n_q, int64_t n_shard, int d);
+/* n_q_limit (optional, device pointer): only the first min(n_q, *n_q_limit) query rows are computed; n_q is then the
+ * capacity the buffers were sized for.  Lets one captured launch serve a per-batch row count known only on the
+ * device (the number of queries of a domain, see c2dsr_eval_partition). */
 int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                           const float* bias, const int64_t* gt, int64_t n_q, int64_t n0, int64_t n1, int d,
-                          int passes, float* s_gt, void* workspace, int64_t workspace_bytes, void* stream);
+                          int passes, const int* n_q_limit, float* s_gt, void* workspace, int64_t workspace_bytes,
+                          void* stream);
 int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                          const float* bias, const float* s_gt, const int64_t* gt, int64_t n_q, int64_t n0,
-                         int64_t n1, int d, int passes, int32_t* counts, float* S_debug, int64_t lds,
-                         void* workspace, int64_t workspace_bytes, void* stream);
+                         int64_t n1, int d, int passes, const int* n_q_limit, int32_t* counts, float* S_debug,
+                         int64_t lds, void* workspace, int64_t workspace_bytes, void* stream);
+/* Evaluation batch on the device, no host round trip (trainer.py:168-179: the per-sample `if xory_last == 0` branch):
+ * stable partition of the B query vectors by domain.  Queries with dom == 0 go, in batch order, to the front of
+ * (QA_hi, QA_lo, gtA), the others to (QB_hi, QB_lo, gtB), already split into bf16 hi / lo (lo may be NULL for
+ * passes == 1); slot[i] = position of query i inside its domain's buffer; n_ab[0 / 1] = queries per domain.  All
+ * buffers have capacity B rows.  workspace: 4 * B + 64 bytes. */
+int c2dsr_eval_partition(const float* q, const int64_t* dom, const int64_t* gt, int64_t B, int d, uint16_t* QA_hi,
+                         uint16_t* QA_lo, uint16_t* QB_hi, uint16_t* QB_lo, int64_t* gtA, int64_t* gtB, int32_t* slot,
+                         int32_t* n_ab, void* stream);
+/* out[i] = (1 + counts of query i in its domain's buffer, dom[i] != 0) as two int32 [B] planes: ranks, domain. */
+int c2dsr_eval_ranks(const int32_t* countsA, const int32_t* countsB, const int32_t* slot, const int64_t* dom, int64_t B,
+                     int32_t* out, void* stream);
 
 /* ---- optimiser -----------------------------------------------------------------------------
  * AdamW with amsgrad on an accumulated gradient (trainer.py:21-22,42,157-158):

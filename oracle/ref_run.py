@@ -79,7 +79,8 @@ def load_trainer(root: str, hp: dict):
         sys.path.insert(0, REF)
     args = reference_args(root, hp)
     torch.manual_seed(args.seed)
-    with warnings.catch_warnings():
+    import contextlib
+    with warnings.catch_warnings(), contextlib.redirect_stdout(sys.stderr):      # (the reference prints progress lines)
         warnings.simplefilter("ignore")
         import trainer as ref_trainer                   # noqa: the reference's module, from oracle/_ref
         tr = ref_trainer.Trainer(args, _Quiet())
@@ -102,7 +103,7 @@ def time_reference(root: str, hp: dict, train_fields: np.ndarray, steps: int, wa
         for i in range(warmup):
             tr.model.convolve_graph()
             tr.train_batch(batches[i % len(batches)])
-        t0, n = time.perf_counter(), 0
+        t0, n, loss = time.perf_counter(), 0, (float("nan"),)
         while n < steps:
             tr.model.convolve_graph()
             loss = tr.train_batch(batches[n % len(batches)])
@@ -110,7 +111,7 @@ def time_reference(root: str, hp: dict, train_fields: np.ndarray, steps: int, wa
             n += 1
             if max_seconds is not None and time.perf_counter() - t0 > max_seconds:
                 break
-        el = time.perf_counter() - t0
+        el = max(time.perf_counter() - t0, 1e-9)
         # evaluation: trainer.py:61-70 on a bounded slice of the validation split (the reference computes the
         # full-domain score vector per query and counts over list_neg: a lower bound for full-catalogue ranking)
         tr.model.eval()

@@ -46,12 +46,26 @@ __device__ __forceinline__ uint32_t sw128(int row, int col) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (col & 7) * 2);
 }
 
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+
 struct Params {
     int mode;      // 0 = SS, 1 = TS
     int n;         // 64, 128, 256
     int b_mn;      // B is MN-major
     int iters;
     int extra_smem_traffic;    // 1: the other warps keep reading shared memory (like TMA writes / epilogues would)
+    int chains;                // independent accumulators the MMAs rotate over (1 = every MMA depends on the previous one)
+    int uniform;               // 1: warp-uniform issue loop + elect.sync; 0: a single lane runs the loop
 };
 
 __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Params p, float* D_out, long long* cycles) {
@@ -87,7 +101,7 @@ __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Params p, float* D_ou
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_a = tmem_base + 256;        // TS: A lives in columns [256, 288)
+    const uint32_t tmem_a = tmem_base + 480;        // TS: A lives in columns [480, 512)
     if (p.mode == 1 && warp < 4) {
         uint32_t r[32];
         const int m = warp * 32 + lane;
@@ -102,7 +116,9 @@ __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Params p, float* D_ou
     __syncthreads();
     tcgen05_fence_after();
     long long t0 = 0, t1 = 0;
-    if (warp == 4 && lane == 0) {
+    if (warp == 4 && (p.uniform || lane == 0)) {
+        // uniform = 1: the WHOLE warp runs the issue loop with identical values and only the instruction itself is
+        // predicated on elect.sync, so descriptors stay in uniform registers (no per-MMA R2UR broadcast loop)
         const uint32_t idesc = make_idesc_bf16(N, false, p.b_mn != 0);
         const uint32_t kb = kstep_units(p.b_mn != 0);
         const uint64_t adesc = make_smem_desc(smem_u32(sA), false), bdesc = make_smem_desc(smem_u32(sB), p.b_mn != 0);
@@ -110,15 +126,19 @@ __global__ void __launch_bounds__(192, 1) mma_bench_kernel(Params p, float* D_ou
         for (int it = 0; it < p.iters; ++it) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const uint32_t acc = (it | k) ? 1u : 0u;
-                if (p.mode == 0) umma_bf16(tmem_base, adesc + 2 * k, bdesc + kb * k, idesc, acc);
-                else umma_bf16_ts(tmem_base, tmem_a + 8 * k, bdesc + kb * k, idesc, acc);
+                const int idx = it * 4 + k;
+                const uint32_t acc = idx >= p.chains ? 1u : 0u;
+                const uint32_t dcol = tmem_base + (uint32_t)((idx & (p.chains - 1)) * N);
+                if (!p.uniform || elect_one()) {
+                    if (p.mode == 0) umma_bf16(dcol, adesc + 2 * k, bdesc + kb * k, idesc, acc);
+                    else umma_bf16_ts(dcol, tmem_a + 8 * k, bdesc + kb * k, idesc, acc);
+                }
             }
         }
-        umma_commit(&bar[0]);
+        if (!p.uniform || elect_one()) umma_commit(&bar[0]);
         mbar_wait(&bar[0], 0);
         t1 = clock64();
-        cycles[blockIdx.x] = t1 - t0;
+        if (lane == 0) cycles[blockIdx.x] = t1 - t0;
     } else if (warp == 5 && p.extra_smem_traffic) {
         // a steady stream of shared-memory reads from another warp while the MMAs run
         volatile uint4* q = reinterpret_cast<volatile uint4*>(sB + 16384);
@@ -158,13 +178,15 @@ int main() {
     std::vector<float> D(128 * 256);
     std::vector<long long> C(sms);
     const int iters = 2000;
-    printf("%-4s %-4s %-5s %-6s %10s %10s %8s %s\n", "mode", "N", "B", "traffic", "clk/MMA", "nominal", "ratio", "numerics");
+    printf("%-4s %-4s %-5s %-6s %10s %10s %8s %s\n", "mode", "N", "B", "chains", "clk/MMA", "nominal", "ratio", "numerics");
     for (int mode = 0; mode < 2; ++mode)
         for (int bmn = 0; bmn < 2; ++bmn)
             for (int n : {64, 128, 256})
-                for (int tr = 0; tr < 2; ++tr) {
-                    Params p{mode, n, bmn, iters, tr};
-                    for (int grid : {1, sms}) {
+                for (int tr : {1, 2, 4, 10, 20}) {
+                    const int chains = tr >= 10 ? tr / 10 : tr, uni = tr >= 10 ? 1 : 0;
+                    if (chains * n > 448) continue;
+                    Params p{mode, n, bmn, iters, 0, chains, uni};
+                    for (int grid : {sms}) {
                         cudaMemset(dD, 0, 128 * 256 * 4);
                         mma_bench_kernel<<<grid, 192, smem_bytes>>>(p, dD, dC);
                         cudaError_t e = cudaDeviceSynchronize();
@@ -175,6 +197,7 @@ int main() {
                         cudaMemcpy(D.data(), dD, 128 * 256 * 4, cudaMemcpyDeviceToHost);
                         cudaMemcpy(C.data(), dC, grid * 8, cudaMemcpyDeviceToHost);
                         double worst = 0;
+                        if (chains == 1)
                         for (int m = 0; m < 128; ++m)
                             for (int j = 0; j < n; ++j) {
                                 long ref = 0;

@@ -97,21 +97,57 @@ def test_main_flags_cover_reference():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU oracle port on the host cores) prints the driver's JSON line: same
-    metric / unit as the GPU arm, impl = reference, e2e without transfers, cpu_baseline describing the run."""
+    """`bench.py --impl reference` (the unmodified reference from oracle/_ref when it is there -- placed by
+    oracle/make_ref.py / __graft_entry__.build() -- else the oracle port) prints the driver's JSON line: same metric /
+    unit / config keys as the GPU arm, impl = reference, exactly the requested steps, e2e without transfers."""
     import json
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
-                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                        "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     z = json.loads(r.stdout.strip().splitlines()[-1])
     assert z["impl"] == "reference" and z["metric"] == "train_seqs_per_sec" and z["unit"] == "seq/s"
-    assert z["value"] > 0 and z["higher_is_better"] is True and z["n_gpus"] == 1 and z["steps"] == 1
+    assert z["value"] > 0 and z["higher_is_better"] is True and z["n_gpus"] == 1 and z["steps"] == 3
     assert z["e2e"] == {"value": z["value"], "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = z["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == z["value"] and "sample" in cb
-    assert "workload" in z["config"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "trainer.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["cores"] >= 1 and cb["value"] == z["value"]
+    assert "3 timed steps" in cb["sample"]
+    # the same workload description as the GPU arm prints (bench.common_config)
+    import argparse
+    import bench
+    import torch
+    hp = bench.hyper(bench.WORKLOADS["tiny"], 0.2, torch.device("cpu"))
+    assert z["config"] == bench.common_config(hp, 0.2, 1)
+
+
+def test_oracle_port_equals_reference_when_present():
+    """oracle/_ref (the unmodified reference, git-ignored) against the oracle port on one seeded tiny step: the port
+    is what the parity tests use, the reference is what the CPU arm times -- they must be the same algorithm."""
+    if not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "trainer.py")):
+        pytest.skip("oracle/_ref not built (run python oracle/make_ref.py where /root/reference exists)")
+    import tempfile
+    import numpy as np
+    import torch
+    import bench
+    import ref_run
+    import c2dsr_oracle as oracle
+    hp = bench.hyper(bench.WORKLOADS["tiny"], 0.0, torch.device("cpu"))
+    adj, fields, ev = bench.make_workload(hp, 2, 1, seed=0)
+    root = tempfile.mkdtemp(prefix="c2dsr_ref_test_")
+    ref_run.write_processed(root, hp.dataset, hp.n_item_a, hp.n_item_b, fields, ev, adj)
+    h = {k: v for k, v in vars(hp).items() if isinstance(v, (int, float, bool, str))}
+    tr, args = ref_run.load_trainer(root, h)
+    otr = oracle.OracleTrainer({k: v.detach().clone() for k, v in tr.model.state_dict().items()},
+                               adj[0].coalesce(), adj[1].coalesce(), h)
+    B = hp.batch_size
+    batch = tuple(torch.from_numpy(np.ascontiguousarray(fields[:B, f])) for f in range(14))
+    tr.model.train(); tr.optimizer.zero_grad(); otr.zero_grad()
+    tr.model.convolve_graph()
+    ref = [float(x) for x in tr.train_batch(batch)]
+    got = [float(x) for x in otr.train_batch(batch, training=True)]
+    np.testing.assert_allclose(got, ref, rtol=2e-6)
 
 
 def test_header_is_plain_c():

@@ -161,7 +161,22 @@ def test_forward_select_equals_forward(d, L, n_head, norm_first):
         full = m(*b)
         ar = torch.arange(B, device=DEV)
         want = [h[ar, s] for h, s in zip(full, sels)]
+        m.pad_pos_zero = False
         got = m.forward_select(*b, *sels)
-    for a, c, nm in zip(got, want, ("share", "a", "b")):
+        # pad-key shortcut: every PAD token has position 0 in preprocessed data, so all allowed keys are one row;
+        # one sequence starts with a real item (a query with no allowed key: attention output 0, Q1b)
+        assert tr.enable_pad_shortcut([ebatch])
+        got_pad = m.forward_select(*b, *sels)
+        seq2 = [x.clone() for x in b]
+        seq2[0][0, 0] = 5; seq2[1][0, 0] = 5; seq2[3][0, 0] = 1; seq2[4][0, 0] = 1
+        sel2 = [s.clone() for s in sels]
+        sel2[0][0] = 0; sel2[1][0] = 0
+        full2 = m(*seq2)
+        got_pad2 = m.forward_select(*seq2, *sel2)
+    for a, a_pad, c, nm in zip(got, got_pad, want, ("share", "a", "b")):
         assert a.shape == c.shape
         assert float((a - c).abs().max()) <= 2e-5 * float(c.abs().max()), nm
+        assert float((a_pad - c).abs().max()) <= 2e-5 * float(c.abs().max()), nm + " (pad-key shortcut)"
+    for a_pad, h, s_, nm in zip(got_pad2, full2, sel2, ("share", "a", "b")):
+        c = h[ar, s_]
+        assert float((a_pad - c).abs().max()) <= 2e-5 * float(c.abs().max()), nm + " (no allowed key)"

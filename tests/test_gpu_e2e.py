@@ -279,7 +279,8 @@ def test_bench_json_contract_on_gpu():
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "eval"):
         assert k in z, k
     assert z["metric"] == "train_seqs_per_sec" and z["unit"] == "seq/s" and z["steps"] == 4 and z["value"] > 0
-    assert z["gpu_launches"] > 0 and z["config"]["cuda_graph_steps"] is True and "workload" in z["config"]
+    assert z["gpu_launches"] > 0 and z["impl"]["cuda_graph_steps"] is True and "workload" in z["config"]
+    assert z["impl"]["eval_pad_key_shortcut"] is True and any("K2 SpMM" in e["kernel"] for e in z["roofline_extra"])
     assert set(z["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and z["e2e"]["h2d_bytes_per_step"] > 0
     assert set(z["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert z["eval"]["value"] > 0
