@@ -10,7 +10,9 @@
 //           dW += dZ^T H (dZ and H MN-major, K = M).  db is a column sum of dZ.
 // All reductions have a fixed order (per-tile partials, K slabs added in order), so results are deterministic.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "tc_host.cuh"
+#include "ce_bwd_fused.cuh"
 #include "../../include/c2dsr_b200.h"
 
 namespace c2dsr {
@@ -271,6 +273,108 @@ static CeLayout ce_layout(void* ws, int64_t M, int64_t N, int d, bool backward) 
     return L;
 }
 
+// ---- fused backward (ce_bwd_fused.cuh): parameter preparation, partial reduction ---------------------------------
+// l2s / cfs / g32 [M_pad] and bl [N_pad], padded with values that make dZ exactly 0 (see CeBwdProblem)
+__global__ void ce_prep_kernel(const float* __restrict__ lse, const float* __restrict__ coef,
+                               const int64_t* __restrict__ gt, const float* __restrict__ bias, int64_t M, int64_t N,
+                               int64_t M_pad, int64_t N_pad, float* __restrict__ l2s, float* __restrict__ cfs,
+                               int* __restrict__ g32, float* __restrict__ bl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M_pad) {
+        bool ok = false;
+        if (i < M) {
+            const int64_t g = gt[i];
+            ok = g >= 0 && g < N;
+            g32[i] = ok ? (int)g : -1;
+        } else {
+            g32[i] = -1;
+        }
+        l2s[i] = ok ? lse[i] * kLog2e : 1e30f;
+        cfs[i] = ok ? coef[i] : 0.f;
+    }
+    if (i < N_pad) bl[i] = i < N ? bias[i] * kLog2e : -1e30f;
+}
+
+// out[x, :] (+)= sum over the partial slabs of x's block, in slab order
+__global__ void ce_part_reduce_kernel(const float* __restrict__ part, int64_t rows, int d, int64_t y_tiles,
+                                      int64_t n_tiles, int64_t grid, int max_slots, float* __restrict__ out,
+                                      int accumulate) {
+    const int64_t total = rows * (int64_t)(d >> 2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t x = i / (d >> 2);
+        const int c = (int)(i - x * (d >> 2)) << 2;
+        const int64_t xb = x / tc::BM;
+        const int64_t c0 = tc::fb_cta_of_tile(xb * y_tiles, n_tiles, grid), c1 = tc::fb_cta_of_tile(xb * y_tiles + y_tiles - 1, n_tiles, grid);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t sl = 0; sl <= c1 - c0; ++sl) {
+            const float4 v = *reinterpret_cast<const float4*>(part + ((xb * max_slots + sl) * tc::BM + (x - xb * tc::BM)) * d + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float4* o = reinterpret_cast<float4*>(out + x * d + c);
+        if (accumulate) {
+            const float4 p = *o;
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        *o = acc;
+    }
+}
+__global__ void ce_db_reduce_kernel(const float* __restrict__ part, int64_t rows, int64_t y_tiles, int64_t n_tiles,
+                                    int64_t grid, int max_slots, float* __restrict__ db) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= rows) return;
+    const int64_t xb = x / tc::BM;
+    const int64_t c0 = tc::fb_cta_of_tile(xb * y_tiles, n_tiles, grid), c1 = tc::fb_cta_of_tile(xb * y_tiles + y_tiles - 1, n_tiles, grid);
+    float s = 0.f;
+    for (int64_t sl = 0; sl <= c1 - c0; ++sl) {
+        const float* p = part + ((xb * max_slots + sl) * 2) * tc::BM + (x - xb * tc::BM);
+        s += p[0] + p[tc::BM];
+    }
+    db[x] += s;
+}
+
+struct FusedLayout {
+    float *l2s, *cfs, *bl, *part_h, *part_w, *db_part;
+    int* g32;
+    int64_t M_pad, N_pad, bytes;
+    int64_t xb_h, yt_h, tiles_h, grid_h, xb_w, yt_w, tiles_w, grid_w;
+    int slots_h, slots_w;
+};
+static int fused_slots(int64_t x_blocks, int64_t y_tiles, int64_t grid) {
+    const int64_t n_tiles = x_blocks * y_tiles;
+    int64_t m = 1;
+    for (int64_t xb = 0; xb < x_blocks; ++xb) {
+        const int64_t c = tc::fb_cta_of_tile(xb * y_tiles + y_tiles - 1, n_tiles, grid) - tc::fb_cta_of_tile(xb * y_tiles, n_tiles, grid) + 1;
+        if (c > m) m = c;
+    }
+    return (int)m;
+}
+static FusedLayout fused_layout(char* p0, int64_t M, int64_t N, int d) {
+    FusedLayout L;
+    char* p = p0;
+    auto take = [&](int64_t bytes) {
+        char* q = p;
+        p += align_up(bytes, 256);
+        return q;
+    };
+    L.M_pad = align_up(M, tc::BM);
+    L.N_pad = align_up(N, tc::BM);
+    L.l2s = (float*)take(L.M_pad * 4); L.cfs = (float*)take(L.M_pad * 4); L.g32 = (int*)take(L.M_pad * 4);
+    L.bl = (float*)take(L.N_pad * 4);
+    const int64_t sms = 148;            // (sizes only; the launch uses the real count, which is not larger on B200)
+    L.xb_h = L.M_pad / tc::BM; L.yt_h = L.N_pad / tc::BM; L.tiles_h = L.xb_h * L.yt_h;
+    L.grid_h = L.tiles_h < sms ? L.tiles_h : sms;
+    L.xb_w = L.N_pad / tc::BM; L.yt_w = L.M_pad / tc::BM; L.tiles_w = L.xb_w * L.yt_w;
+    L.grid_w = L.tiles_w < sms ? L.tiles_w : sms;
+    L.slots_h = fused_slots(L.xb_h, L.yt_h, L.grid_h);
+    L.slots_w = fused_slots(L.xb_w, L.yt_w, L.grid_w);
+    L.part_h = (float*)take(L.xb_h * L.slots_h * tc::BM * (int64_t)d * 4);
+    L.part_w = (float*)take(L.xb_w * L.slots_w * tc::BM * (int64_t)d * 4);
+    L.db_part = (float*)take(L.xb_w * L.slots_w * 2 * tc::BM * 4);
+    L.bytes = p - p0;
+    return L;
+}
+static bool fused_ok(int d) { return d <= tc::ARES_MAX_KB * tc::BK && d % 8 == 0; }
+
 }  // namespace c2dsr
 
 using namespace c2dsr;
@@ -318,6 +422,8 @@ static SideStream& side_stream() {
 extern "C" {
 
 int64_t c2dsr_score_ce_tc_workspace_bytes(int64_t M, int64_t N, int d, int backward) {
+    if (backward && fused_ok(d))      // fused backward: no dZ, no K slabs -- the operand splits + the partial slabs
+        return ce_layout(nullptr, M, N, d, false).bytes + fused_layout(nullptr, M, N, d).bytes + 1024;
     return ce_layout(nullptr, M, N, d, backward != 0).bytes + 1024;
 }
 
@@ -370,8 +476,9 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
         return C2DSR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CeLayout L = ce_layout(workspace, M, N, d, true);
     const bool split = passes == 3;
+    const bool fused = fused_ok(d) && !getenv("C2DSR_CE_BWD_UNFUSED");
+    CeLayout L = ce_layout(workspace, M, N, d, !fused);
     uint16_t* dz_lo = split ? L.dz_lo : nullptr;
     RUN(split_rows(H, M, d, d, L.h_hi, split ? L.h_lo : nullptr, st));
     if (W_hi && (W_lo || !split)) {
@@ -379,6 +486,42 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
         L.w_lo = const_cast<uint16_t*>(W_lo);
     } else {
         RUN(split_rows(W, N, d, d, L.w_hi, split ? L.w_lo : nullptr, st));
+    }
+    if (fused) {
+        // dZ never reaches HBM: two launches of ce_bwd_kernel recompute the logits tile by tile, turn each tile into
+        // dZ inside tensor memory and feed it straight back to the tensor cores (see ce_bwd_fused.cuh)
+        FusedLayout F = fused_layout((char*)workspace + align_up(L.bytes, 256), M, N, d);
+        const int64_t np = F.M_pad > F.N_pad ? F.M_pad : F.N_pad;
+        ce_prep_kernel<<<(unsigned)ceil_div(np, 256), 256, 0, st>>>(lse, coef, gt, bias, M, N, F.M_pad, F.N_pad, F.l2s, F.cfs,
+                                                                    F.g32, F.bl);
+        dzpad_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, st>>>(zpad, lse, coef, gt, M, N, dzpad);
+        note_launches(2);
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(tc::ce_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FB_SMEM);
+            cudaFuncSetAttribute(tc::ce_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FB_SMEM);
+            attr = true;
+        }
+        {   // dH: X = H (stationary), Y = W (streamed)
+            tc::Maps maps;
+            RUN(make_maps<tc::BM>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
+            tc::CeBwdProblem pb{M, N, d, passes, F.l2s, F.cfs, F.g32, F.bl, F.part_h, nullptr, F.slots_h};
+            tc::ce_bwd_kernel<false><<<(unsigned)F.grid_h, tc::THREADS, tc::FB_SMEM, st>>>(maps, pb);
+            ce_part_reduce_kernel<<<ew_grid(M * (int64_t)(d / 4)), 256, 0, st>>>(F.part_h, M, d, F.yt_h, F.tiles_h, F.grid_h,
+                                                                              F.slots_h, dH, 0);
+        }
+        {   // dW, db: X = W (stationary), Y = H (streamed)
+            tc::Maps maps;
+            RUN(make_maps<tc::BM>(&maps, L.w_hi, L.w_lo, N, d, L.h_hi, L.h_lo, M, d, d, passes));
+            tc::CeBwdProblem pb{N, M, d, passes, F.l2s, F.cfs, F.g32, F.bl, F.part_w, F.db_part, F.slots_w};
+            tc::ce_bwd_kernel<true><<<(unsigned)F.grid_w, tc::THREADS, tc::FB_SMEM, st>>>(maps, pb);
+            ce_part_reduce_kernel<<<ew_grid(N * (int64_t)(d / 4)), 256, 0, st>>>(F.part_w, N, d, F.yt_w, F.tiles_w, F.grid_w,
+                                                                              F.slots_w, dW, 1);
+            ce_db_reduce_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, st>>>(F.db_part, N, F.yt_w, F.tiles_w, F.grid_w,
+                                                                         F.slots_w, dbias);
+        }
+        note_launches(5);
+        return check_launch("score_ce_bwd_tc (fused)");
     }
     // 1. recompute the logits, emit dZ [M, N] as bf16 hi / lo
     {
