@@ -347,6 +347,8 @@ def run_b200(a):
         # ---- training, inputs resident in HBM: batches sliced on the device by the package's BatchLoader ----
         ds.to(dev)
         dev_tb = list(loader)
+        for b in dev_tb:             # every rank feeds its own sequences: the global batch of a step is B x world
+            b.global_rows = b.global_batch = B * world
         model.train()
         tr.optimizer.zero_grad()
         step = train_step(dev_tb)
@@ -405,7 +407,9 @@ def run_b200(a):
                 rows_frac = sum(ma * na + mb * nb for ma, mb in used) / (len(used) * (2.0 * B * R) * (na + nb))
         flops_step = flops_ref * rows_frac                               # work the path actually needs
         ach = flops_step / (dom_ms / 1e3) / 1e12
-        units = tr.k4a_gemm_units() if hasattr(tr, "k4a_gemm_units") else 4.0    # logits-sized GEMMs issued / step
+        # logits-sized GEMMs issued per step for the 3 algorithmic ones: forward, then (d <= 256, fused backward) the
+        # logits recomputed in each of the two backward kernels + dZ W + dZ^T H = 5; older path (d > 256): 4
+        units = 5.0 if (a.score_path == "tc" and d <= 256) else 4.0
         out.update({"value": round(train_value, 2), "ms_per_step": round(ms / a.steps, 4), "clocks": clocks,
                     "e2e": {"value": round(train_e2e, 2), "unit": "seq/s",
                             "h2d_bytes_per_step": sum(x.numel() * x.element_size() for x in host_tb[0]),
@@ -429,7 +433,9 @@ def run_b200(a):
             "executed_tflops": round(ach * (units / 3.0) * a.tc_passes, 1) if a.score_path == "tc" else round(ach, 1),
             "executed_frac": round(ach * (units / 3.0) * a.tc_passes / pk["tensor"], 4) if a.score_path == "tc" else None,
             "ms_per_step": round(dom_ms, 4), "share_of_step": round(dom_ms / (ms / a.steps), 4),
-            "path": ("tcgen05 bf16x%d" % a.tc_passes) if a.score_path == "tc" else "ffma fp32 (materialised logits)"}
+            "path": ("tcgen05 bf16x%d: fused log-sum-exp forward; backward = two fused kernels (logits recomputed, dZ kept "
+                     "in tensor memory, dH / dW accumulated in tensor memory)" % a.tc_passes)
+            if a.score_path == "tc" else "ffma fp32 (materialised logits)"}
 
         # ---- the HBM-bound kernels on their own (CUDA events around the entry points, eager launches) ----
         nnz = [int(model.graph_share.nnz), int(model.graph_specific.nnz)]
@@ -478,14 +484,22 @@ def run_b200(a):
         if hp.eval_only:
             n_ev = max(n_ev, a.steps)
         ev_fn = lambda batches: (lambda i: tr.evaluate_batch(batches[i % len(batches)]))
+
+        def ev_run(batches, n):
+            # the trainer's own evaluation loop (run_epoch / run_test use it): ranks of every batch as Python lists,
+            # the host one batch ahead of the device
+            def once(_):
+                for _ranks in tr.evaluate_stream(batches[i % len(batches)] for i in range(n)):
+                    pass
+            return once
         for i in range(max(3, a.warmup)):
             ev_fn(dev_eb)(i)
         l0 = _cabi.launch_count()
         clk = ClockSampler(local_rank)
-        ms_ev = timed(ev_fn(dev_eb), n_ev, world)
+        ms_ev = timed(ev_run(dev_eb, n_ev), 1, world)
         clocks_ev = clk.stop()
         ev_launches = _cabi.launch_count() - l0
-        ms_ev_e2e = timed(ev_fn(host_eb), n_ev, world)
+        ms_ev_e2e = timed(ev_run(host_eb, n_ev), 1, world)
         # the ranking kernels alone: eager launches with events around the two entry points
         use_graph, tr.use_graph = tr.use_graph, False
         ev_prof = profiled({"c2dsr_score_count_tc", "c2dsr_score_target_tc", "c2dsr_score_shard",

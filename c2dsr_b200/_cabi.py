@@ -83,6 +83,7 @@ _PROTOS = {
     "c2dsr_score_tc_workspace_bytes": (i64, [i64, i64, i32]),
     "c2dsr_score_target_tc": (i32, [vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, i64, vp]),
     "c2dsr_score_count_tc": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, i64, vp, i64, vp]),
+    "c2dsr_score_target_full_tc": (i32, [vp, vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, i64, vp]),
     "c2dsr_eval_partition": (i32, [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "c2dsr_eval_ranks": (i32, [vp, vp, vp, vp, i64, vp, vp]),
     "c2dsr_adamw_amsgrad": (i32, [vp, i32, i64, f32, f32, f32, f32, f32, i32, vp]),

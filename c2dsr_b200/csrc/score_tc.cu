@@ -105,6 +105,25 @@ __global__ void gather_target_rows_kernel(const uint16_t* __restrict__ W_hi, con
     if (threadIdx.x == 0) bias_gt[i] = own ? bias[g - n0] : 0.f;
 }
 
+// The same from the fp32 classifier itself (every rank holds all of it): G = split(W[gt]), for EVERY query, whatever
+// shard owns the target -- bit-identical to gathering from the shard's split (same split2), and the target scores
+// then need no exchange between the catalogue shards.
+__global__ void gather_target_rows_f32_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                              const int64_t* __restrict__ gt, int64_t n_items, int d,
+                                              uint16_t* __restrict__ G_hi, uint16_t* __restrict__ G_lo,
+                                              float* __restrict__ bias_gt) {
+    const int64_t i = blockIdx.x;
+    const int64_t g = gt[i];
+    const bool ok = g >= 0 && g < n_items;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        uint16_t h = 0, l = 0;
+        if (ok) split2(W[g * d + c], h, l);
+        G_hi[i * d + c] = h;
+        if (G_lo) G_lo[i * d + c] = l;
+    }
+    if (threadIdx.x == 0) bias_gt[i] = ok ? bias[g] : 0.f;
+}
+
 // ---- epilogues -----------------------------------------------------------------------------------
 struct CountEpilogue {
     const float* bias;       // [N] shard-local
@@ -298,6 +317,33 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
     float* bias_gt = (float*)(G_lo + rows * d);
     gather_target_rows_kernel<<<(unsigned)n_q, 128, 0, st>>>(W_hi, passes == 3 ? W_lo : nullptr, bias, gt, n_q, n0, n1,
                                                              d, G_hi, passes == 3 ? G_lo : nullptr, bias_gt);
+    note_launches(1);
+    tc::Maps maps;
+    RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
+    tc::Problem pb{n_q, n_q, d, passes, 1, 1, n_q_limit};
+    DiagEpilogue epi{bias_gt, s_gt, n_q};
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, st);
+    return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, st);
+}
+
+int c2dsr_score_target_full_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const float* W, const float* bias,
+                               const int64_t* gt, int64_t n_q, int64_t n_items, int d, int passes, const int* n_q_limit,
+                               float* s_gt, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (n_q <= 0) return C2DSR_OK;
+    RUN(c2dsr_device_check());
+    C2DSR_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+    C2DSR_REQUIRE(d % 8 == 0, "d must be a multiple of 8");
+    if (workspace_bytes < c2dsr_score_tc_workspace_bytes(n_q, n_items, d)) {
+        set_error("score_target_full_tc: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t rows = align_up(n_q, tc::BM);
+    uint16_t* G_hi = (uint16_t*)workspace;
+    uint16_t* G_lo = G_hi + rows * d;
+    float* bias_gt = (float*)(G_lo + rows * d);
+    gather_target_rows_f32_kernel<<<(unsigned)n_q, 128, 0, st>>>(W, bias, gt, n_items, d, G_hi, passes == 3 ? G_lo : nullptr,
+                                                                 bias_gt);
     note_launches(1);
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));

@@ -132,3 +132,121 @@ class FlatShards:
             self.flat.copy_(torch.cat(parts))
         else:
             dist.all_gather_into_tensor(self.flat, self.param_shard)
+
+
+class ShardedStep:
+    """Data-parallel optimiser step, version 2: every LARGE parameter tensor (embedding tables, classifier
+    matrices: 98 % of the bytes) goes through its own pipeline on a communication stream --
+
+        reduce-scatter of its gradient (straight from the tensor autograd produced: no 268 MB copy into a bucket)
+        -> AdamW-amsgrad on this rank's 1 / world slice (with the slice of the per-epoch gradient sum, Q2)
+        -> in-place all-gather of the updated slices into the parameter tensor
+
+    -- and the pipelines of the classifier matrices start from a post-accumulate-grad hook, i.e. right after the
+    K4a backward produced their gradients: their whole update is hidden behind the encoder / gather / GCN backward
+    (nothing reads the classifier weights again in that step).  The embedding-table gradients only exist at the
+    end of the backward; their three pipelines alternate between two streams so that the AdamW of one overlaps
+    the collectives of the next.  The small tensors (encoder weights, biases: 2 %) share one flat bucket as
+    before (``FlatShards``).  All of it is stream-ordered and is captured into the step's CUDA graph."""
+
+    BIG = 1 << 20
+
+    def __init__(self, params, rank: int, world_size: int, optimizer, early=()):
+        from ._cabi import AdamTensor, ptr
+        self.rank, self.world_size, self.opt = rank, world_size, optimizer
+        params = list(params)
+        self.big = []
+        small = []
+        for p in params:
+            if p.numel() >= self.BIG and p.numel() % (world_size * 4) == 0 and p.is_contiguous():
+                per = p.numel() // world_size
+                flat = p.data.view(-1)
+                z = lambda: torch.zeros(per, dtype=torch.float32, device=p.device)
+                st = dict(p=p, per=per, flat=flat, pshard=flat[rank * per:(rank + 1) * per], gshard=z(), m=z(), v=z(),
+                          vmax=z(), gsum=z(), done=False, idx=len(self.big))
+                host = (AdamTensor * 1)()
+                host[0].p, host[0].g, host[0].acc = ptr(st["pshard"]), ptr(st["gshard"]), ptr(st["gsum"])
+                host[0].m, host[0].v, host[0].vmax = ptr(st["m"]), ptr(st["v"]), ptr(st["vmax"])
+                host[0].n = per
+                st["table"] = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(p.device)
+                self.big.append(st)
+            else:
+                small.append(p)
+        self.small = FlatShards(small, rank, world_size) if small else None
+        self.streams = tuple(torch.cuda.Stream() for _ in self.big)
+        self._used = set()
+        self.params = params
+        early = {id(p) for p in early}
+        self._hooks = []
+        for st in self.big:
+            if id(st["p"]) in early:
+                self._hooks.append(st["p"].register_post_accumulate_grad_hook(lambda p, st=st: self._pipeline(st)))
+
+    def _stream_of(self, st):
+        idx = st["idx"]
+        self._used.add(idx)
+        stream = self.streams[idx]
+        stream.wait_stream(torch.cuda.current_stream())
+        return stream
+
+    def _reduce(self, st, stream):
+        g = st["p"].grad
+        with torch.cuda.stream(stream):
+            if g is None:
+                st["gshard"].zero_()
+                dist.all_reduce(st["gshard"], op=dist.ReduceOp.SUM)       # (keeps the collective count equal on all ranks)
+            else:
+                dist.reduce_scatter_tensor(st["gshard"], g.contiguous().view(-1), op=dist.ReduceOp.SUM)
+
+    def _update(self, st, stream):
+        from ._cabi import call, ptr
+        group = self.opt.param_groups[0]
+        b1, b2 = group["betas"]
+        with torch.cuda.stream(stream):
+            call("c2dsr_adamw_amsgrad_dyn", ptr(st["table"]), 1, st["per"], ptr(self.opt.dyn_state), b1, b2, group["eps"],
+                 group["weight_decay"], stream.cuda_stream)
+
+    def _gather(self, st, stream):
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(st["flat"], st["pshard"])
+        st["done"] = True
+
+    def _pipeline(self, st):
+        """The whole update of one tensor (post-accumulate-grad hook of the classifier matrices)."""
+        if st["done"]:
+            return
+        stream = self._stream_of(st)
+        self._reduce(st, stream)
+        self._update(st, stream)
+        self._gather(st, stream)
+
+    def finish(self):
+        """End of the backward: the tensors whose update has not started yet (the embedding tables), each on a
+        stream of its own.  Kernels only overlap when SMs are free, and an AdamW launch fills the GPU: so ALL
+        reduce-scatters are launched first (a collective kernel takes a few dozen CTAs), then the AdamW slices --
+        each starts when its own reduce-scatter is done and runs beside the later ones -- then the all-gathers; last
+        the small-tensor bucket on the caller's stream, and the join of the communication streams."""
+        todo = [(st, self._stream_of(st)) for st in self.big if not st["done"]]
+        for st, stream in todo:
+            self._reduce(st, stream)
+        for st, stream in todo:
+            self._update(st, stream)
+        for st, stream in todo:
+            self._gather(st, stream)
+        if self.small is not None:
+            self.opt.step_flat(self.small.param_shard, self.small.reduce_scatter_grads())
+            self.small.all_gather_params()
+        else:
+            self.opt.n_steps += 1
+        cur = torch.cuda.current_stream()
+        for i in sorted(self._used):                  # (only streams that carry work of this step: capture-safe)
+            cur.wait_stream(self.streams[i])
+        self._used.clear()
+        for st in self.big:
+            st["done"] = False
+        for p in self.params:
+            p.grad = None
+
+    def zero_grad_sums(self):
+        for st in self.big:
+            st["gsum"].zero_()

@@ -97,6 +97,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 torch._foreach_zero_(sums)
         if self.__dict__.get("_flat") is not None:
             self._flat["gsum"].zero_()
+        if self.__dict__.get("sharded") is not None:      # data parallel: per-tensor slices of the gradient sums
+            self.sharded.zero_grad_sums()
 
     @torch.no_grad()
     def step(self, closure=None, grads: Optional[Dict[torch.nn.Parameter, torch.Tensor]] = None):

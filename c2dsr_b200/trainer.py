@@ -136,8 +136,7 @@ class Trainer(object):
         pred_a, pred_b = [], []
         with torch.no_grad():
             self.model.convolve_graph()
-            for batch in self.valloader:
-                ra, rb = self.evaluate_batch(batch)
+            for ra, rb in self.evaluate_stream(self.valloader):
                 pred_a += ra
                 pred_b += rb
         return pred_a, pred_b
@@ -147,8 +146,7 @@ class Trainer(object):
         self.model.eval()
         pred_a, pred_b = [], []
         with torch.no_grad():
-            for batch in self.testloader:
-                ra, rb = self.evaluate_batch(batch)
+            for ra, rb in self.evaluate_stream(self.testloader):
                 pred_a += ra
                 pred_b += rb
         return pred_a, pred_b
@@ -244,11 +242,12 @@ class Trainer(object):
             # buffer, all-gather the parameters (dist.FlatShards)
             if self.shards is None:
                 live = [p for p in self.optimizer.param_groups[0]["params"] if p.grad is not None]
-                self.shards = cdist.FlatShards(live, self.rank, self.world_size)
-            self.optimizer.step_flat(self.shards.param_shard, self.shards.reduce_scatter_grads())
-            self.shards.all_gather_params()
-            for p in self.shards.params:
-                p.grad = None
+                m = self.model
+                early = [] if getattr(self.args, "shared_item_embed", False) and False else \
+                    [m.classifier_a.weight, m.classifier_b.weight]
+                self.shards = cdist.ShardedStep(live, self.rank, self.world_size, self.optimizer, early=early)
+                self.optimizer.sharded = self.shards
+            self.shards.finish()
             call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
             out = torch.stack((loss.detach(), loss_rec.detach(), loss_mi.detach()))
             cdist.allreduce_sum_(out)
@@ -448,18 +447,16 @@ class Trainer(object):
              ptr(gts[0]), ptr(gts[1]), ptr(slot), ptr(n_ab), stream())
         s_gt = torch.zeros(2, cap, dtype=torch.float32, device=dev)
         counts = torch.zeros(2, cap, dtype=torch.int32, device=dev)
-        jobs = []
         for k, (cls, Q_hi, Q_lo) in enumerate(((self.model.classifier_a, QA_hi, QA_lo),
                                                (self.model.classifier_b, QB_hi, QB_lo))):
-            n0, n1 = cdist.shard_bounds(cls.weight.shape[0], self.rank, self.world_size)
+            # target scores of all queries from the replicated fp32 classifier: no exchange between the shards
+            W, bias_full = cls.weight.detach(), cls.bias.detach()
+            ws = workspace.get(query("c2dsr_score_tc_workspace_bytes", cap, W.shape[0], d), dev)
+            call("c2dsr_score_target_full_tc", ptr(Q_hi), ptr(Q_lo), ptr(W), ptr(bias_full), ptr(gts[k]), cap, W.shape[0], d,
+                 self.tc_passes, ptr(n_ab[k:]), ptr(s_gt[k]), ptr(ws), ws.numel(), stream())
+            n0, n1 = cdist.shard_bounds(W.shape[0], self.rank, self.world_size)
             W_hi, W_lo = self._split_cache(cls.weight, n0, n1)
-            bias = cls.bias.detach()[n0:n1].contiguous()
-            ws = workspace.get(query("c2dsr_score_tc_workspace_bytes", cap, n1 - n0, d), dev)
-            call("c2dsr_score_target_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(gts[k]), cap, n0, n1,
-                 d, self.tc_passes, ptr(n_ab[k:]), ptr(s_gt[k]), ptr(ws), ws.numel(), stream())
-            jobs.append((Q_hi, Q_lo, W_hi, W_lo, bias, n0, n1))
-        cdist.allreduce_sum_(s_gt)                         # the owner shard's score + zeros (exact)
-        for k, (Q_hi, Q_lo, W_hi, W_lo, bias, n0, n1) in enumerate(jobs):
+            bias = bias_full[n0:n1].contiguous()
             call("c2dsr_score_count_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(s_gt[k]), ptr(gts[k]),
                  cap, n0, n1, d, self.tc_passes, ptr(n_ab[k:]), ptr(counts[k]), None, 0, None, 0, stream())
         cdist.allreduce_sum_(counts)                       # integer partial counts: order independent, bit-exact
@@ -467,7 +464,49 @@ class Trainer(object):
         call("c2dsr_eval_ranks", ptr(counts[0]), ptr(counts[1]), ptr(slot), ptr(dom), Bg, ptr(out), stream())
         return out
 
-    def _evaluate_fused(self, batch):
+    def evaluate_stream(self, batches):
+        """(rank_a, rank_b) for every batch of ``batches``, in order -- like evaluate_batch in a loop, but the host runs
+        one batch ahead of the device: the inputs of batch i + 1 are copied and its graph is replayed before the ranks
+        of batch i are read (pinned double buffer + event), so no device idle time is spent on the per-batch
+        device -> host read that the reference's list-of-ints contract asks for."""
+        pending = None
+        for batch in batches:
+            handle = self._evaluate_launch(batch)
+            if pending is not None:
+                yield self._evaluate_collect(pending)
+            pending = handle
+        if pending is not None:
+            yield self._evaluate_collect(pending)
+
+    @torch.no_grad()
+    def _evaluate_launch(self, batch):
+        fused = self.full_catalog and self.score_path == "tc" and batch[0].shape[0] > 0 and \
+            self.model.attn_share.n_layers == 1 and self.model.hi_share is not None and self.use_graph
+        if not fused:
+            return ("done", self.evaluate_batch(batch))
+        out = self._evaluate_fused(batch, raw=True)
+        if not isinstance(out, torch.Tensor):
+            return ("done", out)
+        k = self._eval_slot = 1 - getattr(self, "_eval_slot", 0)
+        bufs = self.__dict__.setdefault("_eval_pinned", {})
+        key = (k, tuple(out.shape))
+        if key not in bufs:
+            bufs[key] = (torch.empty(out.shape, dtype=out.dtype, pin_memory=True), torch.cuda.Event())
+        host, ev = bufs[key]
+        host.copy_(out, non_blocking=True)
+        ev.record()
+        return ("wait", host, ev)
+
+    @staticmethod
+    def _evaluate_collect(handle):
+        if handle[0] == "done":
+            return handle[1]
+        _, host, ev = handle
+        ev.synchronize()
+        r = host.numpy()
+        return r[0][r[1] == 0].tolist(), r[0][r[1] != 0].tolist()
+
+    def _evaluate_fused(self, batch, raw=False):
         m = self.model
         f = tuple(batch[:10])
         key = (tuple(f[0].shape), m.hi_share.data_ptr(), m.hi_a.data_ptr(), m.hi_b.data_ptr(), self.tc_passes)
@@ -492,6 +531,8 @@ class Trainer(object):
             s_.copy_(x, non_blocking=True)
         g["graph"].replay()
         _cabi.REPLAYED_LAUNCHES += g["launches"]
+        if raw:
+            return g["out"]                                 # (evaluate_stream reads it one batch later)
         r = g["out"].cpu().numpy()                          # the batch's one device -> host read
         return r[0][r[1] == 0].tolist(), r[0][r[1] != 0].tolist()
 

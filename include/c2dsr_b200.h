@@ -251,6 +251,11 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
                           const float* bias, const int64_t* gt, int64_t n_q, int64_t n0, int64_t n1, int d,
                           int passes, const int* n_q_limit, float* s_gt, void* workspace, int64_t workspace_bytes,
                           void* stream);
+/* Target scores of ALL queries from the full fp32 classifier (replicated on every rank): same arithmetic and bits as
+ * c2dsr_score_target_tc on the owning shard, without the exchange between catalogue shards. */
+int c2dsr_score_target_full_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const float* W, const float* bias,
+                               const int64_t* gt, int64_t n_q, int64_t n_items, int d, int passes, const int* n_q_limit,
+                               float* s_gt, void* workspace, int64_t workspace_bytes, void* stream);
 int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint16_t* W_hi, const uint16_t* W_lo,
                          const float* bias, const float* s_gt, const int64_t* gt, int64_t n_q, int64_t n0,
                          int64_t n1, int d, int passes, const int* n_q_limit, int32_t* counts, float* S_debug,
