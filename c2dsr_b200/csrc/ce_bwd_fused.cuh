@@ -42,19 +42,6 @@ struct CeBwdProblem {
     int max_slots;
 };
 
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
-        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 // two fp32 -> one register of two bf16 (low half = first value), round to nearest even
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     uint32_t r;
@@ -286,6 +273,16 @@ ce_bwd_kernel(const __grid_constant__ Maps maps, const CeBwdProblem pb) {
                     l2_row = __ldg(pb.l2s + row);
                     cf_row = __ldg(pb.cfs + row);
                     g_row = __ldg(pb.g32 + row);
+                }
+            }
+            {   // the per-column parameters of this tile: start the loads before waiting for S
+                const int64_t c0 = y_tile * BM + part * 64;
+                if (TRANSPOSED) {
+                    prefetch_l1(pb.l2s + c0); prefetch_l1(pb.l2s + c0 + 32);
+                    prefetch_l1(pb.cfs + c0); prefetch_l1(pb.cfs + c0 + 32);
+                    prefetch_l1(pb.g32 + c0); prefetch_l1(pb.g32 + c0 + 32);
+                } else {
+                    prefetch_l1(pb.bl + c0); prefetch_l1(pb.bl + c0 + 32);
                 }
             }
             mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));

@@ -6,9 +6,12 @@
 // Backward is a scatter-add of token rows g[t] into table rows, made deterministic without sorting and
 // without float atomics:
 //   * item rows: integer atomics elect, per item, the first token that references it and count the
-//     references.  An item referenced once (the common case) is written by that token's warp.  An item
-//     referenced several times is summed by its first token's warp, which scans the token list and adds
-//     the matching rows in token order.
+//     references.  An item referenced once (the common case) is written by that token's warp.  For an item
+//     referenced several times the tokens are bucketed: the elected token reserves a run of a token list
+//     (one atomicAdd of the item's count), every token appends itself to its item's run (slot from an integer
+//     atomic: any order), and the elected token's warp sorts the run (rank by counting, in registers) and adds the
+//     rows in ascending token order.  Runs longer than a warp (an item more than 32 times in one batch) fall back
+//     to a scan of the token list, also in token order.
 //   * the pad row (about half of all tokens) and the positional rows (at most len_max of them, every token
 //     contributes to one) are dense reductions: tokens are cut into fixed chunks, each chunk accumulates
 //     its (len_max + 1) bins in shared memory in token order, and a second kernel adds the chunk partials
@@ -59,10 +62,32 @@ __global__ void mark_kernel(const int64_t* __restrict__ seq, int64_t n_tok, int6
     atomicAdd(cnt + k, 1);
 }
 
+// the elected (first) token of every item referenced more than once reserves cnt[item] slots of the token list
+__global__ void list_alloc_kernel(const int64_t* __restrict__ seq, int64_t n_tok, int64_t pad,
+                                  const int32_t* __restrict__ first, const int32_t* __restrict__ cnt,
+                                  int32_t* __restrict__ start, int32_t* __restrict__ total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tok) return;
+    const int64_t k = seq[t];
+    if (k == pad || first[k] != (int32_t)t || cnt[k] < 2) return;
+    start[k] = atomicAdd(total, cnt[k]);
+}
+// every token of such an item appends itself to the item's run (order inside the run is arbitrary: sorted later)
+__global__ void list_fill_kernel(const int64_t* __restrict__ seq, int64_t n_tok, int64_t pad,
+                                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ start,
+                                 int32_t* __restrict__ fill, int32_t* __restrict__ list) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tok) return;
+    const int64_t k = seq[t];
+    if (k == pad || cnt[k] < 2) return;
+    list[start[k] + atomicAdd(fill + k, 1)] = (int32_t)t;
+}
+
 // one warp per token; lane l owns features l, l+32, ... (d <= 512)
 __global__ void item_rows_kernel(const float* __restrict__ dx, const int64_t* __restrict__ seq, int64_t n_tok, int d,
                                  int64_t pad, float scale, Dropout dr, const int32_t* __restrict__ first,
-                                 const int32_t* __restrict__ cnt, float* d_hi, float* d_E) {
+                                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ start,
+                                 const int32_t* __restrict__ list, float* d_hi, float* d_E) {
     const int lane = threadIdx.x & 31;
     const int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n_tok) return;
@@ -80,8 +105,19 @@ __global__ void item_rows_kernel(const float* __restrict__ dx, const int64_t* __
             if (k < nper && f < d) acc[k] += scale * __ldg(row + f) * drop_scale(dr, (uint64_t)tok * d + f);
         }
     };
-    if (cnt[key] == 1) {
+    const int n_ref = cnt[key];
+    if (n_ref == 1) {
         add_row(t);
+    } else if (n_ref <= 32) {
+        // the item's run of the token list: one entry per lane, rank by counting (entries are distinct), then the
+        // rows are added in ascending token order
+        const int32_t mine = lane < n_ref ? list[start[key] + lane] : 0x7fffffff;
+        int rank = 0;
+        for (int j = 0; j < n_ref; ++j) rank += __shfl_sync(0xffffffffu, mine, j) < mine ? 1 : 0;
+        for (int r = 0; r < n_ref; ++r) {
+            const unsigned m = __ballot_sync(0xffffffffu, lane < n_ref && rank == r);
+            add_row(__shfl_sync(0xffffffffu, mine, __ffs(m) - 1));
+        }
     } else {
         // scan the token list from t on (earlier tokens cannot match); 8 independent 256-byte loads in flight
         for (int64_t base = t & ~(int64_t)31; base < n_tok; base += 32 * 8) {
@@ -184,7 +220,9 @@ int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int6
 
 int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d, int64_t n_rows, int len_max) {
     if (n_tok <= 0) return 256;
-    return align_up(2 * n_rows * 4, 256) + ceil_div(n_tok, kTokChunk) * (int64_t)(len_max + 1) * d * 4 + 256;
+    // first / cnt / start / fill per item, the token list + its allocation counter, then the dense-bin partials
+    return align_up(4 * n_rows * 4, 256) + align_up((n_tok + 64) * 4, 256) +
+           ceil_div(n_tok, kTokChunk) * (int64_t)(len_max + 1) * d * 4 + 256;
 }
 
 int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, float* d_hi, float* d_E, float* d_P,
@@ -205,12 +243,20 @@ int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, fl
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* first = (int32_t*)workspace;
     int32_t* cnt = first + n_rows;
-    float* partial = (float*)((char*)workspace + align_up(2 * n_rows * 4, 256));
+    int32_t* start = cnt + n_rows;
+    int32_t* fill = start + n_rows;
+    int32_t* list = (int32_t*)((char*)workspace + align_up(4 * n_rows * 4, 256));
+    int32_t* total = list + n_tok;
+    float* partial = (float*)((char*)list + align_up((n_tok + 64) * 4, 256));
     cudaMemsetAsync(first, 0x7f, n_rows * 4, st);
-    cudaMemsetAsync(cnt, 0, n_rows * 4, st);
-    mark_kernel<<<(unsigned)ceil_div(n_tok, 256), 256, 0, st>>>(seq, n_tok, pad_idx, first, cnt);
+    cudaMemsetAsync(cnt, 0, 3 * n_rows * 4, st);                  // cnt, start, fill
+    cudaMemsetAsync(total, 0, 4, st);
+    const unsigned tb = (unsigned)ceil_div(n_tok, 256);
+    mark_kernel<<<tb, 256, 0, st>>>(seq, n_tok, pad_idx, first, cnt);
+    list_alloc_kernel<<<tb, 256, 0, st>>>(seq, n_tok, pad_idx, first, cnt, start, total);
+    list_fill_kernel<<<tb, 256, 0, st>>>(seq, n_tok, pad_idx, cnt, start, fill, list);
     item_rows_kernel<<<(unsigned)ceil_div(n_tok, 8), 256, 0, st>>>(dx, seq, n_tok, d, pad_idx, scale, dr, first, cnt,
-                                                                  d_hi, d_E);
+                                                                  start, list, d_hi, d_E);
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(bin_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -221,7 +267,7 @@ int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, fl
         dx, seq, pos, n_tok, d, len_max, pad_idx, scale, dr, partial);
     bin_reduce_kernel<<<(unsigned)ceil_div((int64_t)(len_max + 1) * d, 256), 256, 0, st>>>(partial, n_chunks, d,
                                                                                           len_max, pad_idx, d_P, d_hi);
-    note_launches(4);
+    note_launches(6);
     return check_launch("gather_bwd");
 }
 

@@ -45,6 +45,9 @@ struct LseEpilogue {
     float m_run, s_run;
     int64_t g, slot;
     __device__ __forceinline__ void tile_begin(int64_t, int64_t n_blk, int64_t row, int, int part) {
+        const int64_t c0 = n_blk * 128 + part * (128 / tc::EPI_PARTS);
+        if (c0 < N) tc::prefetch_l1(bias + c0);
+        if (c0 + 32 < N) tc::prefetch_l1(bias + c0 + 32);
         m_run = -INFINITY;
         s_run = 0.f;
         slot = n_blk * tc::EPI_PARTS + part;                 // one (max, sum) pair per row, tile and column part
@@ -450,10 +453,10 @@ int c2dsr_score_ce_fwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
     }
     tc::Maps maps;
     RUN(make_maps<kBN1>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
-    tc::Problem pb{M, N, d, passes, 0, 1};
+    tc::Problem pb{M, N, d, passes, 0, 1, L.h_hi, L.h_lo, d};
     LseEpilogue epi{bias, gt, L.pmax, L.psum, L.zgt, M, N, L.n_pairs, 0.f, 0.f, 0, 0};
     if (d <= tc::ARES_MAX_KB * tc::BK) {     // the H row block stays resident in shared memory
-        RUN((launch_gemm<kBN1, kStages1, true, false, false>(maps, pb, epi, st)));
+        RUN((launch_gemm<kBN1, tc::ARES_STAGES, true, false, false>(maps, pb, epi, st)));
     } else {
         RUN((launch_gemm<kBN1, kStages1, false, false, false>(maps, pb, epi, st)));
     }
@@ -527,10 +530,10 @@ int c2dsr_score_ce_bwd_tc(const float* H, const float* W, const uint16_t* W_hi, 
     {
         tc::Maps maps;
         RUN(make_maps<kBN1>(&maps, L.h_hi, L.h_lo, M, d, L.w_hi, L.w_lo, N, d, d, passes));
-        tc::Problem pb{M, N, d, passes, 0, 1};
+        tc::Problem pb{M, N, d, passes, 0, 1, L.h_hi, L.h_lo, d};
         GradEpilogue epi{bias, gt, lse, coef, L.dz_hi, dz_lo, M, N, L.ldn, 0.f, 0.f, 0};
         if (d <= tc::ARES_MAX_KB * tc::BK) {
-            RUN((launch_gemm<kBN1, kStages1, true, false, false>(maps, pb, epi, st)));
+            RUN((launch_gemm<kBN1, tc::ARES_STAGES, true, false, false>(maps, pb, epi, st)));
         } else {
             RUN((launch_gemm<kBN1, kStages1, false, false, false>(maps, pb, epi, st)));
         }

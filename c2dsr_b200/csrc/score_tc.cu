@@ -125,6 +125,7 @@ __global__ void gather_target_rows_f32_kernel(const float* __restrict__ W, const
 }
 
 // ---- epilogues -----------------------------------------------------------------------------------
+constexpr int kBNc = 128;        // tile width of the kernels these epilogues run in
 struct CountEpilogue {
     const float* bias;       // [N] shard-local
     const float* s_gt;       // [M]
@@ -135,8 +136,11 @@ struct CountEpilogue {
     float tgt;
     int64_t g_local;
     int cnt;
-    __device__ __forceinline__ void tile_begin(int64_t, int64_t, int64_t row, int, int) {
+    __device__ __forceinline__ void tile_begin(int64_t, int64_t n_blk, int64_t row, int, int part) {
         cnt = 0;
+        const int64_t c0 = n_blk * kBNc + part * (kBNc / tc::EPI_PARTS);
+        if (c0 < N) tc::prefetch_l1(bias + c0);
+        if (c0 + 32 < N) tc::prefetch_l1(bias + c0 + 32);
         if (row < M) {
             tgt = s_gt[row];
             g_local = gt[row] - n0;
@@ -320,9 +324,9 @@ int c2dsr_score_target_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint
     note_launches(1);
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
-    tc::Problem pb{n_q, n_q, d, passes, 1, 1, n_q_limit};
+    tc::Problem pb{n_q, n_q, d, passes, 1, 1, Q_hi, Q_lo, d, n_q_limit};
     DiagEpilogue epi{bias_gt, s_gt, n_q};
-    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, st);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, tc::ARES_STAGES, true, false, false>(maps, pb, epi, st);
     return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, st);
 }
 
@@ -347,9 +351,9 @@ int c2dsr_score_target_full_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const
     note_launches(1);
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, G_hi, G_lo, n_q, d, d, passes));
-    tc::Problem pb{n_q, n_q, d, passes, 1, 1, n_q_limit};
+    tc::Problem pb{n_q, n_q, d, passes, 1, 1, Q_hi, Q_lo, d, n_q_limit};
     DiagEpilogue epi{bias_gt, s_gt, n_q};
-    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, st);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, tc::ARES_STAGES, true, false, false>(maps, pb, epi, st);
     return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, st);
 }
 
@@ -365,10 +369,10 @@ int c2dsr_score_count_tc(const uint16_t* Q_hi, const uint16_t* Q_lo, const uint1
     const int64_t n = n1 - n0;
     tc::Maps maps;
     RUN(make_maps<kBN>(&maps, Q_hi, Q_lo, n_q, d, W_hi, W_lo, n, d, d, passes));
-    tc::Problem pb{n_q, n, d, passes, 0, 1, n_q_limit};
+    tc::Problem pb{n_q, n, d, passes, 0, 1, Q_hi, Q_lo, d, n_q_limit};
     CountEpilogue epi{bias, s_gt, gt, counts, S_debug, lds, n_q, n, n0, 0.f, 0, 0};
     // the queries' row block stays resident in shared memory when it fits (d <= 256); same MMA sequence either way
-    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, kStages, true, false, false>(maps, pb, epi, (cudaStream_t)stream);
+    if (d <= tc::ARES_MAX_KB * tc::BK) return launch_gemm<kBN, tc::ARES_STAGES, true, false, false>(maps, pb, epi, (cudaStream_t)stream);
     return launch_gemm<kBN, kStages, false, false, false>(maps, pb, epi, (cudaStream_t)stream);
 }
 

@@ -16,9 +16,13 @@
 // Two operand-staging modes:
 //   ARES = false  every k-block stage holds A and B tiles (any K; used for the long-K gradient GEMMs,
 //                 optionally split along K into slabs whose partial sums the caller adds in order)
-//   ARES = true   the whole A row block (all k-blocks, hi and lo) stays resident in shared memory while
-//                 the CTA walks consecutive N tiles, so only B is streamed: half the L2->SM traffic of
-//                 the streaming mode.  Needs K <= 256 (the logits / score GEMMs with d <= 256).
+//   ARES = true   the whole A row block (all k-blocks, hi and lo) stays resident in TENSOR MEMORY (256 columns:
+//                 bf16 pairs packed along K, one row per lane; tcgen05.mma reads A from TMEM) while the CTA
+//                 walks consecutive N tiles.  Only B is streamed, and ALL of shared memory is ring: 7 stages of
+//                 32 KB instead of 3, i.e. ~190 KB of B tiles in flight -- what it takes to cover the TMA latency
+//                 at 42 B/clk/SM (with 3 stages the MMA warp waited on `full` half the time).  The epilogue
+//                 warps load a new row block (global -> registers -> tcgen05.st) when it changes.  Needs
+//                 K <= 256 and BN = 128 (the logits / score GEMMs with d <= 256).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -32,6 +36,7 @@ constexpr int BM = 128;        // rows of A per tile = TMEM lanes
 constexpr int BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom
 constexpr int UMMA_K = 16;
 constexpr int ARES_MAX_KB = 4; // resident A: up to 4 k-blocks (K <= 256)
+constexpr int ARES_STAGES = 7; // ring depth of the resident-A kernels (BN = 128: 7 x 32 KB)
 constexpr int EPI_WARPS = 8;   // epilogue warps: two per TMEM lane quarter, each takes half of the tile's columns
 constexpr int EPI_PARTS = EPI_WARPS / 4;
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
@@ -42,6 +47,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// start fetching the line at p into L1 (the epilogues ask for the per-column parameters of a tile before they wait for
+// its accumulator, so the L2 round trip overlaps the MMAs instead of stalling the first add of every chunk)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -223,6 +232,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // 128-byte swizzled operand tiles, both built from 128-byte smem rows (tile base 1024-B aligned):
 //   K-major   row = one M/N index, 64 consecutive K elements inside the row (TMA box 64 k x rows).
 //             8 rows form a swizzle atom: SBO = 1024 B; LBO unused; the next UMMA_K = 16 elements are +32 B.
@@ -258,6 +280,9 @@ struct Problem {
     int passes;         // 3 = hi/lo split, 1 = hi only
     int diag_only;      // 1: only tiles with m_blk == n_blk (target-score pass, BN == BM)
     int k_splits;       // >= 1: K is cut into this many slabs; the epilogue receives the slab index
+    const uint16_t* a_hi_ptr;   // resident-A mode: the bf16 hi / lo matrices of A themselves ([M, lda], K-major)
+    const uint16_t* a_lo_ptr;
+    int64_t lda;
     const int* m_limit; // optional device-resident row count: only the first min(M, *m_limit) rows of A are computed
                         // (M stays the capacity the tensor maps and the launch were sized for; lets a captured
                         // launch follow a row count that is only known on the device)
@@ -267,7 +292,7 @@ template <int BN, int STAGES, bool ARES>
 struct SmemLayout {
     static constexpr int A_TILE = BM * BK * 2;           // 16 KB
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int A_RES = ARES ? ARES_MAX_KB * 2 * A_TILE : 0;     // resident A row block (hi, lo)
+    static constexpr int A_RES = 0;                       // (the resident A row block lives in tensor memory)
     static constexpr int STAGE = (ARES ? 0 : 2 * A_TILE) + 2 * B_TILE;
     static constexpr int B_OFF = ARES ? 0 : 2 * A_TILE;   // offset of B_hi inside a stage
     static constexpr int RING_OFF = A_RES;
@@ -285,36 +310,6 @@ __device__ __forceinline__ void dispatch_index(int v, F&& f) {
     } else {
         if (v == N - 1) f(std::integral_constant<int, N - 1>{});
         else dispatch_index<N - 1>(v, f);
-    }
-}
-
-// the 4 (passes = 1) or 12 (passes = 3) MMAs of one 64-wide k-block
-template <int BN, int STAGES, bool ARES, bool A_MN, bool B_MN, int STAGE, int ACC, int KB>
-__device__ __forceinline__ void issue_kblock(uint32_t smem_base, uint32_t tmem_base, bool split, uint32_t accum0) {
-    using L = SmemLayout<BN, STAGES, ARES>;
-    constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
-    constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
-    constexpr uint32_t st_off = (uint32_t)(L::RING_OFF + STAGE * L::STAGE);
-    constexpr uint32_t a_off = ARES ? (uint32_t)(KB * 2 * L::A_TILE) : st_off;
-    constexpr uint32_t b_off = st_off + (uint32_t)L::B_OFF;
-    constexpr uint32_t lbo_a = (uint32_t)(A_MN ? (BK * 128) >> 4 : 1) << 16, lbo_b = (uint32_t)(B_MN ? (BK * 128) >> 4 : 1) << 16;
-    // (smem_base is 1024-byte aligned and below 256 KB: the address field of base + offset is the sum of the fields)
-    const uint32_t base16 = (smem_base & 0x3FFFFu) >> 4;
-    const uint32_t a_hi = (base16 + (a_off >> 4)) | lbo_a, a_lo = a_hi + (uint32_t)(L::A_TILE >> 4);
-    const uint32_t b_hi = (base16 + (b_off >> 4)) | lbo_b, b_lo = b_hi + (uint32_t)(L::B_TILE >> 4);
-    const uint32_t d_tmem = tmem_base + (uint32_t)(ACC * BN);
-    if (split) {          // small cross terms first, then the leading product
-        umma_lo_elect(d_tmem, a_lo, b_hi, idesc, accum0);
-#pragma unroll
-        for (int k = 1; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, 1u);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, 1u);
-    } else {
-        umma_lo_elect(d_tmem, a_hi, b_hi, idesc, accum0);
-#pragma unroll
-        for (int k = 1; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, 1u);
     }
 }
 
@@ -409,11 +404,14 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             mbar_init(&tmem_full[s], 1);
             mbar_init(&tmem_empty[s], EPI_WARPS);
         }
-        mbar_init(a_full, 1);
+        mbar_init(a_full, EPI_WARPS);      // (resident A is written by the epilogue warps)
         mbar_init(a_empty, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, 2 * BN);
+    constexpr uint32_t TMEM_COLS = ARES ? 512 : 2 * BN;   // resident A: hi in columns [256, 384), lo in [384, 512)
+    constexpr uint32_t A_TMEM = 256;
+    static_assert(!ARES || BN == 128, "the resident-A mode is laid out for BN = 128");
+    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
@@ -449,16 +447,6 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             int slab, kb0, kb1;
             tile_coords(t, m_blk, n_blk, slab);
             kb_range(slab, kb0, kb1);
-            if (ARES && m_blk != cur_m) {
-                mbar_wait(a_empty, a_phase ^ 1);              // MMAs of the previous row block are done
-                mbar_arrive_expect_tx_elect(a_full, (uint32_t)n_kb_total * (uint32_t)L::A_TILE * (split ? 2u : 1u));
-                for (int kb = 0; kb < n_kb_total; ++kb) {
-                    load_a(&maps.a_hi, a_full, smem + kb * 2 * L::A_TILE, kb, m_blk);
-                    if (split) load_a(&maps.a_lo, a_full, smem + kb * 2 * L::A_TILE + L::A_TILE, kb, m_blk);
-                }
-                a_phase ^= 1;
-                cur_m = m_blk;
-            }
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* st = ring + stage * L::STAGE;
@@ -489,7 +477,8 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
             kb_range(slab, kb0, kb1);
             if (ARES && m_blk != cur_m) {
                 if (cur_m >= 0) umma_commit_elect(a_empty);          // previous row block no longer needed
-                mbar_wait(a_full, a_phase);
+                mbar_wait(a_full, a_phase);                          // the epilogue warps have stored the new one
+                tcgen05_fence_after();
                 a_phase ^= 1;
                 cur_m = m_blk;
             }
@@ -500,25 +489,30 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
                 tcgen05_fence_after();
                 // descriptor low words from the (warp-uniform) stage / k-block counters: uniform-datapath arithmetic
                 const uint32_t st = smem_base + (uint32_t)(L::RING_OFF + stage * L::STAGE);
-                const uint32_t a_base = ARES ? smem_base + (uint32_t)(kb * 2 * L::A_TILE) : st;
-                const uint32_t a_hi = desc_lo(a_base, A_MN), a_lo = a_hi + (uint32_t)(L::A_TILE >> 4);
+                const uint32_t a_hi = ARES ? tmem_base + A_TMEM + (uint32_t)(kb * (BK / 2)) : desc_lo(st, A_MN);
+                const uint32_t a_lo = ARES ? a_hi + 128u : a_hi + (uint32_t)(L::A_TILE >> 4);
                 const uint32_t b_hi = desc_lo(st + L::B_OFF, B_MN), b_lo = b_hi + (uint32_t)(L::B_TILE >> 4);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 constexpr uint32_t idesc = make_idesc_bf16(BN, A_MN, B_MN);
-                constexpr uint32_t ka = kstep_units(A_MN), kbs = kstep_units(B_MN);
+                // per UMMA_K slice: A advances 8 TMEM columns (16 bf16) or one descriptor k-step
+                constexpr uint32_t ka = ARES ? (uint32_t)(UMMA_K / 2) : kstep_units(A_MN), kbs = kstep_units(B_MN);
+                auto mma = [&](uint32_t a, uint32_t b, uint32_t accumulate) {
+                    if (ARES) umma_ts_lo_elect(d_tmem, a, b, idesc, accumulate);
+                    else umma_lo_elect(d_tmem, a, b, idesc, accumulate);
+                };
                 uint32_t accum = kb > kb0 ? 1u : 0u;
                 if (split) {      // small cross terms first, then the leading product
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_lo_elect(d_tmem, a_lo + ka * k, b_hi + kbs * k, idesc, accum);
+                        mma(a_lo + ka * k, b_hi + kbs * k, accum);
                         accum = 1u;
                     }
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) umma_lo_elect(d_tmem, a_hi + ka * k, b_lo + kbs * k, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) mma(a_hi + ka * k, b_lo + kbs * k, 1u);
                 }
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_lo_elect(d_tmem, a_hi + ka * k, b_hi + kbs * k, idesc, accum);
+                    mma(a_hi + ka * k, b_hi + kbs * k, accum);
                     accum = 1u;
                 }
                 umma_commit_elect(&empty[stage]);          // smem stage is free once these MMAs retire
@@ -539,12 +533,43 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
         const int part = (warp - 4) >> 2;            // which column range of the tile
         constexpr int PART_COLS = BN / EPI_PARTS;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, a_phase_epi = 0;
+        int64_t cur_m_epi = -1;
         for (int64_t t = t0; t < t1; ++t) {
             int64_t m_blk, n_blk;
             int slab;
             tile_coords(t, m_blk, n_blk, slab);
             const int64_t row = m_blk * BM + q * 32 + lane;
+            if (ARES && m_blk != cur_m_epi) {
+                // resident A: this thread's row of the new block, bf16 pairs as stored (K-major), into its TMEM
+                // lane; the `part` 0 warps store the hi half (columns [256, 384)), the `part` 1 warps the lo half
+                if (cur_m_epi >= 0) {
+                    mbar_wait(a_empty, a_phase_epi);             // every MMA that read the previous block is done
+                    a_phase_epi ^= 1;
+                    tcgen05_fence_after();
+                }
+                cur_m_epi = m_blk;
+                const uint16_t* src = part == 0 ? pb.a_hi_ptr : pb.a_lo_ptr;
+                const bool live = row < pb.M && (part == 0 || split);
+                const uint4* r4 = reinterpret_cast<const uint4*>(src + row * pb.lda);
+                const int n_vec = pb.K >> 3;                     // 16-byte vectors in the row (K % 8 == 0)
+                const uint32_t a_addr = tmem_base + ((uint32_t)(q * 32) << 16) + A_TMEM + (uint32_t)(part * 128);
+#pragma unroll 1
+                for (int c = 0; c < ARES_MAX_KB; ++c) {          // 32 columns = 64 bf16 = one k-block per store
+                    uint32_t w[32];
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const int vi = c * 8 + v;
+                        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                        if (live && vi < n_vec) x = __ldg(r4 + vi);
+                        w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+                    }
+                    tmem_st32(a_addr + (uint32_t)(32 * c), w);
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full);
+            }
             epi.tile_begin(m_blk, n_blk, row, slab, part);
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
@@ -569,7 +594,7 @@ gemm_kernel(const __grid_constant__ Maps maps, const Problem pb, Epilogue epi) {
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
