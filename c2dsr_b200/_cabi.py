@@ -57,6 +57,8 @@ _PROTOS = {
     "c2dsr_encoder_fwd_select": (i32, [vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32, vp, vp, i64,
                                        vp]),
     "c2dsr_encoder_padkeys_workspace_bytes": (i64, [i64, i32, i32]),
+    "c2dsr_encoder_padkeys_prepare": (i32, [vp, i32, vp, i32, i32, f32, vp, vp, i64, vp]),
+    "c2dsr_gather_select_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, f32, i64, vp]),
     "c2dsr_encoder_fwd_padkeys": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32, vp, vp,
                                         i64, vp]),
     "c2dsr_encoder_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, i32, i64, i32, i32, f32] + _DROP

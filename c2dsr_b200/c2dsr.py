@@ -124,6 +124,11 @@ class C2DSR(nn.Module):
         # set by the Trainer once it has checked on the host that every PAD token of the evaluation splits has
         # position 0: forward_select() may then use the pad-key shortcut (ops.branch_padkeys)
         self.pad_pos_zero = False
+        self._pad_cache = {}
+
+    def train(self, mode: bool = True):
+        self._pad_cache = {}            # (weights may change while training: the evaluation shortcut's vectors are stale)
+        return super().train(mode)
 
     def _apply(self, fn, *a, **k):
         """.to()/.cuda(): the CSR graphs follow the parameters; cached propagations are dropped."""
@@ -147,6 +152,7 @@ class C2DSR(nn.Module):
         by the branches that consume them, each on its own stream, inside forward_all (and cached as usual)."""
         s = self._next_seed()
         self._share_calls = 0
+        self._pad_cache = {}            # evaluation shortcut: per-branch PAD-token vectors of these propagated tables
         if lazy and self.branch_streams and torch.is_grad_enabled() and self.embed_i.weight.is_cuda \
                 and self.gnn_share.n_gnn >= 1:
             self._gcn_lazy = s
@@ -207,9 +213,13 @@ class C2DSR(nn.Module):
             if st is not cur:
                 st.wait_stream(cur)
             with torch.cuda.stream(st):
-                fn = ops.branch_padkeys if (self.pad_pos_zero and not self.training) else ops.branch_select
-                outs[i] = fn(hi, table.weight, attn.pos_emb.weight, seq, pos, sel, float(self.d_latent ** 0.5),
-                             self.n_item - 1, attn.n_head, attn.norm_first, attn.dense_passes_eval, attn.weights())
+                a = (hi, table.weight, attn.pos_emb.weight, seq, pos, sel, float(self.d_latent ** 0.5), self.n_item - 1,
+                     attn.n_head, attn.norm_first, attn.dense_passes_eval, attn.weights())
+                if self.pad_pos_zero and not self.training:
+                    # (the PAD token's attention output is cached per branch until the next convolve_graph())
+                    outs[i] = ops.branch_padkeys(*a, cache=self._pad_cache.setdefault(i, {}))
+                else:
+                    outs[i] = ops.branch_select(*a)
         for st in self._side[:2]:
             cur.wait_stream(st)
         return tuple(outs)

@@ -986,8 +986,37 @@ int64_t c2dsr_encoder_padkeys_workspace_bytes(int64_t n_seq, int d, int dense_pa
     return (6 * n_seq + 8) * (int64_t)d * 4 + kGemmWsBytes + (dense_passes ? dense_tc_bytes(n_seq, d) : 0) + 1024;
 }
 
+// the PAD token's attention-block output y_pad [d] of a one-layer encoder: value projection of x_pad, then the output
+// projection (exact fp32).  It depends on the weights and on the propagated PAD row only, not on the batch.
+int c2dsr_encoder_padkeys_prepare(const c2dsr_layer_weights* layers, int n_layers, const float* x_pad, int d,
+                                  int norm_first, float eps, float* y_pad, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+    C2DSR_REQUIRE(n_layers == 1, "the pad-key forward covers one encoder layer");
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0 && d <= 32 * kMaxPerLane, "d must be a multiple of 4 in (0, 512]");
+    if (workspace_bytes < (int64_t)(8 * d) * 4 + kGemmWsBytes) {
+        set_error("encoder_padkeys_prepare: workspace too small");
+        return C2DSR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    float* pad_in = (float*)workspace;
+    float* pad_qkv = pad_in + d;
+    void* gws = pad_qkv + 4 * d;
+    const Dropout none = make_dropout(0.f, 0, 0);
+    const c2dsr_layer_weights& w = layers[0];
+    const float* attn_in = x_pad;
+    if (norm_first) {
+        RUN(launch_add_ln(x_pad, nullptr, w.ln1_w, w.ln1_b, nullptr, pad_in, nullptr, 1, d, 1, eps, none, st));
+        attn_in = pad_in;
+    }
+    RUN(dense(0, nullptr, 0, 0, 1, 1, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, pad_qkv, 3 * d, w.in_proj_b, 0, none,
+              gws, kGemmWsBytes, st));
+    RUN(dense(0, nullptr, 0, 0, 1, 1, d, d, 1.f, pad_qkv + 2 * d, d, w.out_proj_w, d, 0.f, y_pad, d, w.out_proj_b, 0, none,
+              gws, kGemmWsBytes, st));
+    return check_launch("encoder_padkeys_prepare");
+}
+
 int c2dsr_encoder_fwd_padkeys(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
-                              const float* x_sel, const float* x_pad, const int64_t* seq, const int64_t* sel,
+                              const float* x_sel, const float* y_pad, const int64_t* seq, const int64_t* sel,
                               int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first,
                               int dense_passes, float eps, float* out, void* workspace, int64_t workspace_bytes,
                               void* stream) {
@@ -1006,25 +1035,12 @@ int c2dsr_encoder_fwd_padkeys(const c2dsr_layer_weights* layers, int n_layers, c
     float* x1 = y + Bd;
     float* t1 = x1 + Bd;
     float* t2 = t1 + Bd;
-    float* pad_in = t2 + 3 * Bd;                // pad token: LayerNorm1(x_pad) (pre-norm), qkv [3d], y_pad [d]
-    float* pad_qkv = pad_in + d;
-    float* pad_y = pad_qkv + 3 * d;
-    void* gws = pad_y + 3 * d;
+    void* gws = t2 + 3 * Bd + 8 * d;
     void* tws = (char*)gws + kGemmWsBytes;
     const int64_t tws_bytes = dense_passes ? dense_tc_bytes(n_seq, d) : 0;
     const Dropout none = make_dropout(0.f, 0, 0);
     const c2dsr_layer_weights& w = layers[0];
-    // the pad token (one row): value projection and output projection, exact fp32
-    const float* attn_in = x_pad;
-    if (norm_first) {
-        RUN(launch_add_ln(x_pad, nullptr, w.ln1_w, w.ln1_b, nullptr, pad_in, nullptr, 1, d, 1, eps, none, st));
-        attn_in = pad_in;
-    }
-    RUN(dense(0, nullptr, 0, 0, 1, 1, 3 * d, d, 1.f, attn_in, d, w.in_proj_w, d, 0.f, pad_qkv, 3 * d, w.in_proj_b, 0, none,
-              gws, kGemmWsBytes, st));
-    RUN(dense(0, nullptr, 0, 0, 1, 1, d, d, 1.f, pad_qkv + 2 * d, d, w.out_proj_w, d, 0.f, pad_y, d, w.out_proj_b, 0, none,
-              gws, kGemmWsBytes, st));
-    padkey_rows_kernel<<<(unsigned)ceil_div(n_seq, 8), 256, 0, st>>>(seq, sel, n_seq, L, d, pad_idx, pad_y, w.out_proj_b,
+    padkey_rows_kernel<<<(unsigned)ceil_div(n_seq, 8), 256, 0, st>>>(seq, sel, n_seq, L, d, pad_idx, y_pad, w.out_proj_b,
                                                                     y);
     note_launches(1);
     // from here on exactly c2dsr_encoder_fwd_select: n_seq rows

@@ -48,6 +48,35 @@ __global__ void gather_fwd_kernel(const float* __restrict__ hi, const float* __r
     }
 }
 
+// evaluation: only position sel[b] of sequence b is needed (plus, as row n_seq, one PAD token at position 0): the
+// same arithmetic as gather_fwd_kernel for those tokens, without the index-gather launches in front of it
+__global__ void gather_select_fwd_kernel(const float* __restrict__ hi, const float* __restrict__ E,
+                                         const float* __restrict__ P, const int64_t* __restrict__ seq,
+                                         const int64_t* __restrict__ pos, const int64_t* __restrict__ sel,
+                                         float* __restrict__ x, int64_t n_seq, int L, int d, float scale, int64_t pad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b > n_seq) return;
+    int64_t item = pad, ps = 0;
+    if (b < n_seq) {
+        const int64_t t = b * L + sel[b];
+        item = seq[t];
+        ps = pos[t];
+    }
+    const float4* h4 = reinterpret_cast<const float4*>(hi + item * d);
+    const float4* e4 = reinterpret_cast<const float4*>(E + item * d);
+    const float4* p4 = reinterpret_cast<const float4*>(P + ps * d);
+    float4* o4 = reinterpret_cast<float4*>(x + b * d);
+    for (int v = lane; v < (d >> 2); v += 32) {
+        float4 a = __ldg(h4 + v), bb = __ldg(e4 + v), c = __ldg(p4 + v), r;
+        r.x = __fadd_rn(__fmul_rn(__fadd_rn(a.x, bb.x), scale), c.x);
+        r.y = __fadd_rn(__fmul_rn(__fadd_rn(a.y, bb.y), scale), c.y);
+        r.z = __fadd_rn(__fmul_rn(__fadd_rn(a.z, bb.z), scale), c.z);
+        r.w = __fadd_rn(__fmul_rn(__fadd_rn(a.w, bb.w), scale), c.w);
+        o4[v] = r;
+    }
+}
+
 // ---- backward -----------------------------------------------------------------------------------
 constexpr int kTokChunk = 64;      // tokens per dense-bin chunk
 constexpr int kSlab = 128;         // features per dense-bin block
@@ -216,6 +245,17 @@ int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int6
         hi, E, P, seq, pos, x, n_tok, d, scale, make_dropout(p, seed, tag));
     note_launches(1);
     return check_launch("gather_fwd");
+}
+
+int c2dsr_gather_select_fwd(const float* hi, const float* E, const float* P, const int64_t* seq, const int64_t* pos,
+                            const int64_t* sel, float* x, int64_t n_seq, int L, int d, float scale, int64_t pad_idx,
+                            void* stream) {
+    if (n_seq < 0) return C2DSR_OK;
+    C2DSR_REQUIRE(d > 0 && d % 4 == 0, "d must be a positive multiple of 4");
+    gather_select_fwd_kernel<<<(unsigned)ceil_div(n_seq + 1, 8), 256, 0, (cudaStream_t)stream>>>(hi, E, P, seq, pos, sel, x,
+                                                                                                 n_seq, L, d, scale, pad_idx);
+    note_launches(1);
+    return check_launch("gather_select_fwd");
 }
 
 int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d, int64_t n_rows, int len_max) {

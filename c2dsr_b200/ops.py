@@ -234,26 +234,33 @@ def branch_select(hi, E, P, seq, pos, sel, scale: float, pad_idx: int, n_head: i
 
 @torch.no_grad()
 def branch_padkeys(hi, E, P, seq, pos, sel, scale: float, pad_idx: int, n_head: int, norm_first: bool,
-                   dense_passes: int, weights):
+                   dense_passes: int, weights, cache=None):
     """Evaluation form of one branch when every PAD token has position 0 (the preprocessor's invariant, checked by
     CDSRDataset.check_bounds): h[b, sel[b], :] without projecting or attending over the B * L tokens at all -- the
     reference's inverted key-padding mask lets a query see PAD keys only, and those are all the same
-    row.  One gather of B + 1 tokens (the selected ones and one PAD token), then c2dsr_encoder_fwd_padkeys."""
+    row.  One gather of B + 1 tokens (the selected ones and one PAD token), then c2dsr_encoder_fwd_padkeys.  ``cache``
+    (a dict owned by the caller, emptied whenever the propagated tables or the weights change) keeps the PAD token's
+    attention-block output, which does not depend on the batch."""
     hi, E, P = _f(hi), _f(E), _f(P)
     seq, pos, sel = seq.contiguous(), pos.contiguous(), sel.contiguous()
     w = [_f(t) for t in weights]
     n_seq, L = seq.shape
     d = E.shape[1]
-    ids = torch.empty(n_seq + 1, dtype=I64, device=seq.device)
-    ps = torch.zeros(n_seq + 1, dtype=I64, device=seq.device)
-    torch.gather(seq, 1, sel.view(-1, 1), out=ids[:n_seq].view(-1, 1))
-    torch.gather(pos, 1, sel.view(-1, 1), out=ps[:n_seq].view(-1, 1))
-    ids[n_seq:].fill_(pad_idx)                                    # (a fill kernel: no host copy)
-    x = _gather_forward(hi, E, P, ids, ps, scale, 0.0, 0, 0)      # [n_seq + 1, d]; the last row is the PAD token
+    x = torch.empty(n_seq + 1, d, device=E.device, dtype=F32)          # the last row is the PAD token
+    call("c2dsr_gather_select_fwd", ptr(hi), ptr(E), ptr(P), ptr(seq, I64), ptr(pos, I64), ptr(sel, I64), ptr(x), n_seq, L,
+         d, scale, pad_idx, stream())
+    table = _layer_table(w, 1)
+    y_pad = cache.get("y_pad") if cache is not None else None
+    if y_pad is None:
+        y_pad = torch.empty(d, device=E.device, dtype=F32)
+        ws = workspace.get(32 * d + (16 << 20) + 1024, E.device)
+        call("c2dsr_encoder_padkeys_prepare", C.addressof(table), 1, ptr(x[n_seq:]), d, int(norm_first), LN_EPS, ptr(y_pad),
+             ptr(ws), ws.numel(), stream())
+        if cache is not None and not torch.cuda.is_current_stream_capturing():
+            cache["y_pad"] = y_pad
     out = torch.empty(n_seq, d, device=E.device, dtype=F32)
     ws = workspace.get(query("c2dsr_encoder_padkeys_workspace_bytes", n_seq, d, dense_passes), E.device)
-    table = _layer_table(w, 1)
-    call("c2dsr_encoder_fwd_padkeys", C.addressof(table), 1, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(x[n_seq:]), ptr(seq, I64),
+    call("c2dsr_encoder_fwd_padkeys", C.addressof(table), 1, ptr(w[-2]), ptr(w[-1]), ptr(x), ptr(y_pad), ptr(seq, I64),
          ptr(sel, I64), n_seq, L, d, n_head, pad_idx, int(norm_first), dense_passes, LN_EPS, ptr(out), ptr(ws),
          ws.numel(), stream())
     return out

@@ -420,7 +420,7 @@ class Trainer(object):
         return counts + 1
 
     # ---- full-catalogue evaluation of a batch entirely on the device (one CUDA graph, one host read) ----------
-    def _eval_fused_body(self, f):
+    def _eval_fused_body(self, f, bufs=None):
         """f = the first ten evaluation fields on the device (global batch, identical on every rank).  Encoders on
         this rank's slice of the queries, all-gather of the query vectors, stable partition by domain on the device
         (c2dsr_eval_partition), per domain the target-score and counting GEMMs over this rank's catalogue shard with
@@ -437,16 +437,23 @@ class Trainer(object):
         q = cdist.allgather_rows(q.contiguous(), Bg)
         split = self.tc_passes == 3
         cap = -(-Bg // 128) * 128
-        bf = lambda: torch.zeros(cap, d, dtype=torch.bfloat16, device=dev)
-        QA_hi, QB_hi = bf(), bf()
-        QA_lo, QB_lo = (bf(), bf()) if split else (None, None)
-        gts = torch.zeros(2, cap, dtype=torch.int64, device=dev)
-        slot = torch.empty(Bg, dtype=torch.int32, device=dev)
-        n_ab = torch.zeros(2, dtype=torch.int32, device=dev)
+        if bufs is None or bufs.get("cap") != (cap, d, split):
+            # scratch of the ranking part; rows past a domain's query count keep stale (finite) values that are never
+            # read back, so nothing but the counts needs clearing per batch
+            bf = lambda: torch.zeros(cap, d, dtype=torch.bfloat16, device=dev)
+            bufs = {} if bufs is None else bufs
+            bufs.update(cap=(cap, d, split), QA_hi=bf(), QB_hi=bf(), QA_lo=bf() if split else None,
+                        QB_lo=bf() if split else None, gts=torch.zeros(2, cap, dtype=torch.int64, device=dev),
+                        slot=torch.zeros(Bg, dtype=torch.int32, device=dev),
+                        n_ab=torch.zeros(2, dtype=torch.int32, device=dev),
+                        s_gt=torch.zeros(2, cap, dtype=torch.float32, device=dev),
+                        counts=torch.zeros(2, cap, dtype=torch.int32, device=dev),
+                        out=torch.empty(2, Bg, dtype=torch.int32, device=dev))
+        QA_hi, QB_hi, QA_lo, QB_lo = bufs["QA_hi"], bufs["QB_hi"], bufs["QA_lo"], bufs["QB_lo"]
+        gts, slot, n_ab, s_gt, counts = bufs["gts"], bufs["slot"], bufs["n_ab"], bufs["s_gt"], bufs["counts"]
         call("c2dsr_eval_partition", ptr(q), ptr(dom), ptr(gt), Bg, d, ptr(QA_hi), ptr(QA_lo), ptr(QB_hi), ptr(QB_lo),
              ptr(gts[0]), ptr(gts[1]), ptr(slot), ptr(n_ab), stream())
-        s_gt = torch.zeros(2, cap, dtype=torch.float32, device=dev)
-        counts = torch.zeros(2, cap, dtype=torch.int32, device=dev)
+        counts.zero_()
         for k, (cls, Q_hi, Q_lo) in enumerate(((self.model.classifier_a, QA_hi, QA_lo),
                                                (self.model.classifier_b, QB_hi, QB_lo))):
             # target scores of all queries from the replicated fp32 classifier: no exchange between the shards
@@ -456,11 +463,11 @@ class Trainer(object):
                  self.tc_passes, ptr(n_ab[k:]), ptr(s_gt[k]), ptr(ws), ws.numel(), stream())
             n0, n1 = cdist.shard_bounds(W.shape[0], self.rank, self.world_size)
             W_hi, W_lo = self._split_cache(cls.weight, n0, n1)
-            bias = bias_full[n0:n1].contiguous()
+            bias = bias_full[n0:n1]
             call("c2dsr_score_count_tc", ptr(Q_hi), ptr(Q_lo), ptr(W_hi), ptr(W_lo), ptr(bias), ptr(s_gt[k]), ptr(gts[k]),
                  cap, n0, n1, d, self.tc_passes, ptr(n_ab[k:]), ptr(counts[k]), None, 0, None, 0, stream())
         cdist.allreduce_sum_(counts)                       # integer partial counts: order independent, bit-exact
-        out = torch.empty(2, Bg, dtype=torch.int32, device=dev)
+        out = bufs["out"]
         call("c2dsr_eval_ranks", ptr(counts[0]), ptr(counts[1]), ptr(slot), ptr(dom), Bg, ptr(out), stream())
         return out
 
@@ -515,7 +522,7 @@ class Trainer(object):
             f_dev = tuple(x.to(self.device, non_blocking=True) for x in f)
             if not self.use_graph or self._eval_seen != key:       # first batch of a shape / phase: eager
                 self._eval_seen = key
-                out = self._eval_fused_body(f_dev)
+                out = self._eval_fused_body(f_dev, self.__dict__.setdefault("_eval_bufs", {}))
                 r = out.cpu().numpy()
                 return r[0][r[1] == 0].tolist(), r[0][r[1] != 0].tolist()
             static = tuple(x.clone() for x in f_dev)
@@ -523,12 +530,19 @@ class Trainer(object):
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             l0 = _cabi.launch_count()
+            bufs = {}
+            self._eval_fused_body(static, bufs)             # (allocates the scratch outside the capture)
+            torch.cuda.synchronize()
             with torch.cuda.graph(graph):
-                out = self._eval_fused_body(static)
-            g = self._eval_graph = dict(key=key, graph=graph, static=static, out=out,
-                                        launches=_cabi.launch_count() - l0)
-        for s_, x in zip(g["static"], f):
-            s_.copy_(x, non_blocking=True)
+                out = self._eval_fused_body(static, bufs)
+            g = self._eval_graph = dict(key=key, graph=graph, static=static, out=out, bufs=bufs,
+                                        keep=[dict(c) for c in m._pad_cache.values()],   # tensors the graph reads
+                                        launches=(_cabi.launch_count() - l0) // 2)
+        if all(x.is_cuda for x in f):
+            torch._foreach_copy_(list(g["static"]), list(f))        # ten fields, one or two launches
+        else:
+            for s_, x in zip(g["static"], f):
+                s_.copy_(x, non_blocking=True)
         g["graph"].replay()
         _cabi.REPLAYED_LAUNCHES += g["launches"]
         if raw:

@@ -47,6 +47,11 @@ int c2dsr_gather_fwd(const float* hi, const float* E, const float* P, const int6
  *   g[t] = dx[t] * mask;  d_P[pos[t]] += g[t];  S[n] = scale * sum_{t: seq[t]=n} g[t];
  *   d_hi[n] += S[n];  d_E[n] += S[n] for n != pad_idx  (nn.Embedding padding_idx, C2DSR.py:20).
  * replaces embedding_dense_backward reached from loss.backward() (trainer.py:156). */
+/* Evaluation: x[b] = the branch input of token (b, sel[b]) for b < n_seq, and x[n_seq] = that of one PAD token at
+ * position 0 (what the pad-key shortcut needs); x is [n_seq + 1, d].  No dropout. */
+int c2dsr_gather_select_fwd(const float* hi, const float* E, const float* P, const int64_t* seq, const int64_t* pos,
+                            const int64_t* sel, float* x, int64_t n_seq, int L, int d, float scale, int64_t pad_idx,
+                            void* stream);
 int64_t c2dsr_gather_bwd_workspace_bytes(int64_t n_tok, int d, int64_t n_rows, int len_max);
 int c2dsr_gather_bwd(const float* dx, const int64_t* seq, const int64_t* pos, float* d_hi, float* d_E, float* d_P,
                      int64_t n_tok, int d, int64_t n_rows, int len_max, int64_t pad_idx, float scale, float p,
@@ -137,10 +142,15 @@ int c2dsr_encoder_fwd_select(const c2dsr_layer_weights* layers_host, int n_layer
  * gives pad tokens position 0; the host checks that once per split).  Identical keys -> uniform soft-max ->
  * the attention output of any query with at least one allowed key is the value row of x_pad; with none it is 0.
  * So: x_sel [n_seq, d] = input rows of the selected tokens, x_pad [d]; seq / sel only decide "has an allowed key".
- * No QKV projection or attention over the n_seq * L tokens is computed at all. */
+ * No QKV projection or attention over the n_seq * L tokens is computed at all.
+ * c2dsr_encoder_padkeys_prepare computes y_pad [d] = out_proj(value_proj(x_pad)) once per propagation (it does not
+ * depend on the batch; workspace >= 32 d bytes + 16 MiB); c2dsr_encoder_fwd_padkeys is the per-batch part. */
 int64_t c2dsr_encoder_padkeys_workspace_bytes(int64_t n_seq, int d, int dense_passes);
+int c2dsr_encoder_padkeys_prepare(const c2dsr_layer_weights* layers, int n_layers, const float* x_pad, int d,
+                                  int norm_first, float eps, float* y_pad, void* workspace, int64_t workspace_bytes,
+                                  void* stream);
 int c2dsr_encoder_fwd_padkeys(const c2dsr_layer_weights* layers, int n_layers, const float* lnf_w, const float* lnf_b,
-                              const float* x_sel, const float* x_pad, const int64_t* seq, const int64_t* sel,
+                              const float* x_sel, const float* y_pad, const int64_t* seq, const int64_t* sel,
                               int64_t n_seq, int L, int d, int n_head, int64_t pad_idx, int norm_first,
                               int dense_passes, float eps, float* out, void* workspace, int64_t workspace_bytes,
                               void* stream);
