@@ -19,7 +19,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(PKG, "libc2dsr_b200.so")
 SOURCES = ["core.cu", "gather.cu", "spmm.cu", "gemm.cu", "encoder.cu", "infomax.cu", "score.cu", "score_tc.cu", "score_ce_tc.cu",
-           "tc_linear.cu", "graph_build.cu", "loss_rows.cu"]
+           "tc_linear.cu", "graph_build.cu", "loss_rows.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -145,6 +145,54 @@ def preprocess_evaluate(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: 
             np.stack(negs) if n else np.zeros((0, n_neg_sample), np.int64))
 
 
+def _flatten(seqs: Sequence[Sequence[int]], len_max: int):
+    lens = np.fromiter((len(u) for u in seqs), np.int64, len(seqs))
+    if len(lens) and int(lens.max()) - 1 > len_max:
+        raise ValueError(f"sequence of {int(lens.max())} items exceeds len_max+1 = {len_max + 1}")
+    if len(lens) and int(lens.min()) < 1:
+        raise ValueError("empty sequence")
+    offs = np.zeros(len(seqs) + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    items = np.fromiter((x for u in seqs for x in u), np.int64, int(offs[-1]))
+    return items, offs
+
+
+def preprocess_train_device(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int, device,
+                            rng=random) -> torch.Tensor:
+    """``preprocess_train`` with the per-sequence work on the GPU ([n_kept, 14, len_max] int64 on ``device``).  The
+    host keeps only what has to follow Python's ``random`` stream: one ``randint`` per input position, in the
+    reference's order (dataloader.py:80,85); note that the reference draws for every sequence, kept or not."""
+    from . import ops
+    pad = n_item_a + n_item_b
+    items, offs = _flatten(seqs, len_max)
+    is_input = np.ones(len(items), bool)
+    is_input[offs[1:] - 1] = False                       # the final target of every sequence gets no draw
+    dom_a = (items[is_input] < n_item_a).tolist()
+    randint, a_hi, b_lo, b_hi = rng.randint, n_item_a - 1, n_item_a, pad - 1
+    draws = np.fromiter((randint(0, a_hi) if a else randint(b_lo, b_hi) for a in dom_a), np.int64, len(dom_a))
+    dev = torch.device(device)
+    fields, keep = ops.preprocess_train(torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev),
+                                        torch.from_numpy(draws).to(dev), n_item_a, n_item_b, len_max)
+    return fields[keep]
+
+
+def preprocess_evaluate_device(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int,
+                               n_neg_sample: int, device, rng=random):
+    """``preprocess_evaluate`` with the per-sequence work on the GPU; the host draws ``rng.sample`` per sequence
+    (dataloader.py:216-224) and nothing else."""
+    from . import ops
+    items, offs = _flatten(seqs, len_max)
+    last = items[offs[1:] - 1] if len(seqs) else np.zeros(0, np.int64)
+    g = np.where(last < n_item_a, last, last - n_item_a)
+    hi = np.where(last < n_item_a, n_item_a, n_item_b - n_item_a)
+    n_pop = (g + np.maximum(0, hi - g - 1)).tolist()
+    sample = rng.sample
+    picks = np.asarray([sample(range(p), n_neg_sample) for p in n_pop], np.int64).reshape(len(seqs), n_neg_sample)
+    dev = torch.device(device)
+    return ops.preprocess_eval(torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev),
+                               torch.from_numpy(picks).to(dev), n_item_a, n_item_b, len_max)
+
+
 class CDSRDataset(torch.utils.data.Dataset):
     """Same constructor and item contract as the reference's ``CDSRDataset`` (dataloader.py:9-37,
     230-234); holds one int64 tensor per field instead of nested lists (``self.fields``)."""
@@ -154,12 +202,16 @@ class CDSRDataset(torch.utils.data.Dataset):
         self.len_max = args.len_max
         if getattr(args, "use_raw", False):
             seqs = read_raw(join(args.path_raw, mode + "_new.txt"))
+            dev = getattr(args, "device", None) if getattr(args, "device_preprocess", False) else None
             if mode == "train":
-                packed = preprocess_train(seqs, args.n_item_a, args.n_item_b, args.len_max)
+                packed = preprocess_train(seqs, args.n_item_a, args.n_item_b, args.len_max) if dev is None else \
+                    preprocess_train_device(seqs, args.n_item_a, args.n_item_b, args.len_max, dev)
                 fields = [packed[:, i] for i in range(14)]
             else:
                 six, four, neg = preprocess_evaluate(seqs, args.n_item_a, args.n_item_b, args.len_max,
-                                                     args.n_neg_sample)
+                                                     args.n_neg_sample) if dev is None else \
+                    preprocess_evaluate_device(seqs, args.n_item_a, args.n_item_b, args.len_max, args.n_neg_sample,
+                                               dev)
                 fields = [six[:, i] for i in range(6)] + [four[:, i:i + 1] for i in range(4)] + [neg]
             if getattr(args, "save_processed", True):
                 with open(join(args.path_data, mode + ".pkl"), "wb") as f:   # the reference's pickle layout
@@ -169,7 +221,8 @@ class CDSRDataset(torch.utils.data.Dataset):
                 data = pickle.load(f)
             n_f = 14 if mode == "train" else 11
             fields = [np.asarray([row[i] for row in data], np.int64).reshape(len(data), -1) for i in range(n_f)]
-        self.fields = [torch.from_numpy(np.ascontiguousarray(x)) for x in fields]
+        self.fields = [x.contiguous() if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x))
+                       for x in fields]
         self.length = len(self.fields[0])
 
     @classmethod

@@ -581,6 +581,30 @@ class DomainLossTcFn(torch.autograd.Function):
         return d_share, d_dom, dW, db, dwpad, dbpad, None, None, None, None, None, None, None
 
 
+def preprocess_train(items, offs, draws, n_item_a: int, n_item_b: int, len_max: int):
+    """Device preprocessor of the training split (dataloader.py:60-161): ``items`` / ``offs`` the concatenated item
+    lists, ``draws`` the host-drawn corruption ids (one per input position).  Returns (fields [n, 14, L] int64 of
+    every sequence, keep [n] bool -- the reference drops the others)."""
+    n = offs.numel() - 1
+    fields = torch.empty(n, 14, len_max, dtype=I64, device=items.device)
+    keep = torch.empty(n, dtype=torch.uint8, device=items.device)
+    call("c2dsr_preprocess_train", ptr(items, I64), ptr(offs, I64), ptr(draws, I64), n, n_item_a, n_item_b, len_max,
+         ptr(fields, I64), ptr(keep), stream())
+    return fields, keep.bool()
+
+
+def preprocess_eval(items, offs, picks, n_item_a: int, n_item_b: int, len_max: int):
+    """Device preprocessor of an evaluation split (dataloader.py:163-228); ``picks`` [n, n_neg] is the host's sample
+    of range(population), turned into the negative ids in place.  Returns (six [n, 6, L], four [n, 4], picks)."""
+    n = offs.numel() - 1
+    six = torch.empty(n, 6, len_max, dtype=I64, device=items.device)
+    four = torch.empty(n, 4, dtype=I64, device=items.device)
+    picks = picks.contiguous()
+    call("c2dsr_preprocess_eval", ptr(items, I64), ptr(offs, I64), n, n_item_a, n_item_b, len_max, picks.shape[1],
+         ptr(six, I64), ptr(four, I64), ptr(picks, I64), stream())
+    return six, four, picks
+
+
 def compact_rows(gt: torch.Tensor, ignore: int) -> torch.Tensor:
     """Stable partition of the row indices: rows with gt != ignore first (int64 [M])."""
     gt = gt.contiguous()

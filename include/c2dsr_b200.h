@@ -347,6 +347,21 @@ int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, i
 /* elementwise glue: out = a*x + b*y (y may be NULL) */
 int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);
 
+/* ---- preprocessor on the device (dataloader.py:60-228) -------------------------------------------------
+ * items / offs: the time-sorted item lists of n_seq sequences, concatenated (sequence u = items[offs[u] .. offs[u+1]),
+ * its last item is the final target).  The random ingredients come from the host, drawn from Python's `random` in
+ * the reference's order: draws[offs[u] - u + i] = the corruption draw of input position i of sequence u
+ * (dataloader.py:80,85); neg [n_seq, n_neg] holds, on entry, the sample of range(population) (dataloader.py:216-224)
+ * and, on return, the negative ids (picks shifted past the target).  Outputs are the reference's fields:
+ * fields [n_seq, 14, len_max] + keep [n_seq] (the reference drops sequences without a target in either domain);
+ * six [n_seq, 6, len_max], four [n_seq, 4] = idx_last_a, idx_last_b, xory_last, gt_last.  All int64. */
+int c2dsr_preprocess_train(const int64_t* items, const int64_t* offs, const int64_t* draws, int64_t n_seq,
+                           int64_t n_item_a, int64_t n_item_b, int len_max, int64_t* fields, uint8_t* keep,
+                           void* stream);
+int c2dsr_preprocess_eval(const int64_t* items, const int64_t* offs, int64_t n_seq, int64_t n_item_a,
+                          int64_t n_item_b, int len_max, int n_neg, int64_t* six, int64_t* four, int64_t* neg,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif
