@@ -266,9 +266,16 @@ def dp_parity(rank, world, local_rank):
     tr.model.train()
     tr.optimizer.zero_grad()
     worst = 0.0
-    for s, batch in enumerate(loader):
-        got = [float(x) for x in tr.train_step(batch)]
-        worst = max(worst, max(abs(a - b) / abs(b) for a, b in zip(got, g.z["losses"][s])))
+    from c2dsr_b200 import dist as cdist
+    big, cdist.ShardedStep.BIG = cdist.ShardedStep.BIG, 4096       # the fixture's tables take the large-tensor path
+    try:
+        for s, batch in enumerate(loader):
+            got = [float(x) for x in tr.train_step(batch)]
+            worst = max(worst, max(abs(a - b) / abs(b) for a, b in zip(got, g.z["losses"][s])))
+    finally:
+        cdist.ShardedStep.BIG = big
+    path = "nccl" if tr.shards.peer is None else ("multimem" if tr.shards.peer["multicast"] else "p2p")
+    n_big = len(tr.shards.big)
     final, d = g.group("final"), hp["d_latent"]
     w_err = 0.0
     for k, p in tr.model.state_dict().items():
@@ -278,8 +285,10 @@ def dp_parity(rank, world, local_rank):
         w_err = max(w_err, rel_err(p.cpu()[sl], final[k][sl]))
     out = {"fixture": "tests/golden/mid_default.npz (reference outputs)", "ranks": world, "steps": n_steps,
            "max_rel_loss_err_vs_reference": float(f"{worst:.3e}"), "max_rel_weight_err_vs_reference": float(f"{w_err:.3e}"),
-           "graph_replayed": bool(tr._graphs), "ok": bool(worst < 1e-4 and w_err < 1e-3)}
+           "graph_replayed": bool(tr._graphs), "dp_step": path, "large_tensors": n_big,
+           "ok": bool(worst < 1e-4 and w_err < 1e-3)}
     tr._graphs.clear()
+    tr.shards.close()
     del tr
     torch.cuda.synchronize()
     return out
@@ -416,6 +425,12 @@ def run_b200(a):
                             "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / a.steps, 4)}})
         impl.update({"cuda_graph_steps": bool(tr._graphs), "priming_steps": priming,
                      "host_enqueue_ms_per_step": round(host_ms, 3)})
+        if world > 1 and tr.shards is not None:
+            peer = tr.shards.peer
+            impl["dp_step"] = ("peer memory: all-reduce + AdamW + broadcast in one kernel (%s)" %
+                               ("multimem over NVSwitch" if peer["multicast"] else "P2P loads / stores")) \
+                if peer is not None else "NCCL reduce-scatter -> AdamW slice -> all-gather per tensor (%s)" % \
+                getattr(tr.shards, "peer_error", "C2DSR_DP=nccl")
         tsrc = os.path.join("profiles", "r02_k4a_traffic.json")
         traffic = None
         if os.path.exists(os.path.join(ROOT, tsrc)) and a.workload == "fk" and a.score_path == "tc" and not a.all_rows:

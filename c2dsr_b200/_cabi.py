@@ -28,6 +28,18 @@ class AdamTensor(C.Structure):
     _fields_ = [("p", vp), ("g", vp), ("acc", vp), ("m", vp), ("v", vp), ("vmax", vp), ("n", i64)]
 
 
+MAX_PEERS = 16
+
+
+class PeerTensor(C.Structure):
+    _fields_ = [("t", AdamTensor), ("offset", i64)]
+
+
+class PeerMap(C.Structure):
+    _fields_ = [("world", i32), ("rank", i32), ("grad", vp * MAX_PEERS), ("param", vp * MAX_PEERS), ("grad_mc", vp),
+                ("param_mc", vp)]
+
+
 # name -> (restype, argtypes); mirrors include/c2dsr_b200.h one to one
 _DROP = [f32, u64, u64]
 _PROTOS = {
@@ -102,6 +114,7 @@ _PROTOS = {
     "c2dsr_adamw_amsgrad_dyn": (i32, [vp, i32, i64, vp, f32, f32, f32, f32, vp]),
     "c2dsr_preprocess_train": (i32, [vp, vp, vp, i64, i64, i64, i32, vp, vp, vp]),
     "c2dsr_preprocess_eval": (i32, [vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, vp]),
+    "c2dsr_adamw_amsgrad_peer": (i32, [vp, i32, i64, vp, vp, f32, f32, f32, f32, vp]),
     "c2dsr_axpby": (i32, [vp, vp, vp, i64, f32, f32, vp]),
 }
 EXPORTS = tuple(_PROTOS)

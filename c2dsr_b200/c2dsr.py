@@ -264,7 +264,8 @@ class C2DSR(nn.Module):
             specs.append(dict(seq=seq, pos=pos, scale=float(self.d_latent ** 0.5), pad=self.n_item - 1,
                               p=attn.p if self.training else 0.0, seed=seed, gather_tag=tag * 2 + 1,
                               encoder_tag=tag * 2, n_head=attn.n_head, norm_first=attn.norm_first,
-                              dense_passes=attn.dense_passes if grad else attn.dense_passes_eval, n_w=len(w)))
+                              dense_passes=attn.dense_passes if grad else attn.dense_passes_eval, n_w=len(w),
+                              table_ptr=table.weight.data_ptr()))
             # hi = GCN(table) of this step: hand the branch the recipe and a detached hi, so that the GCN
             # backward runs inside the branch (on its stream, with the direct-lookup gradient folded in)
             rec = self._gcn_rec.get(id(hi)) if (grad and hi is not None) else None

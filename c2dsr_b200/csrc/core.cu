@@ -217,6 +217,94 @@ __global__ void adamw_kernel(const c2dsr_adam_tensor* __restrict__ table, float 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Data-parallel optimiser step over peer memory: gradient all-reduce, AdamW and parameter broadcast in ONE kernel.
+// Every rank owns 1 / world of each large tensor.  For an element of its slice the kernel
+//   - sums the gradient over the ranks: one multimem.ld_reduce on the multicast address of the gradient blocks
+//     (the NVSwitch adds the eight copies and returns one value), or, without multicast, peer loads in rank order;
+//   - applies AdamW-amsgrad with the slice's state (same arithmetic as adamw_kernel);
+//   - stores the new value into every rank's parameter block: one multimem.st, or world peer stores.
+// NVLink carries each gradient byte once and each new parameter byte once per direction, reads and writes in
+// flight together; the host brackets the launch with device-side barriers over all ranks (dist.PeerStep).
+__device__ __forceinline__ float4 mc_ld_reduce(const float* addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float* addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 peer_ld(const float* addr) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_st(float* addr, float4 v) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool MC>
+__global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor* __restrict__ table,
+                                                         const __grid_constant__ c2dsr_peer_map map, float beta1,
+                                                         float beta2, float eps, float wd,
+                                                         const c2dsr_step_state* __restrict__ state) {
+    __shared__ float bc[2];
+    if (threadIdx.x == 0) {
+        const double n = (double)state->step;
+        bc[0] = (float)(1.0 / (1.0 - pow((double)beta1, n)));
+        bc[1] = (float)sqrt(1.0 - pow((double)beta2, n));
+    }
+    __syncthreads();
+    const float lr = state->lr, inv_bc1 = bc[0], sqrt_bc2 = bc[1];
+    const c2dsr_peer_tensor job = table[blockIdx.y];
+    const c2dsr_adam_tensor t = job.t;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float decay = 1.f - lr * wd;
+    const float step_size = lr * inv_bc1;
+    auto update = [&](float g, float& p, float& m, float& v, float& vm) {
+        p *= decay;
+        m = m + (g - m) * (1.f - beta1);
+        v = v * beta2 + (1.f - beta2) * g * g;
+        vm = fmaxf(vm, v);
+        p -= step_size * (m / (sqrtf(vm) / sqrt_bc2 + eps));
+    };
+    const int64_t n4 = t.n >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int64_t e = job.offset + i * 4;
+        float4 gn;
+        if (MC) {
+            gn = mc_ld_reduce(map.grad_mc + e);
+        } else {
+            gn = peer_ld(map.grad[0] + e);
+            for (int k = 1; k < map.world; ++k) {
+                const float4 x = peer_ld(map.grad[k] + e);
+                gn.x += x.x; gn.y += x.y; gn.z += x.z; gn.w += x.w;
+            }
+        }
+        float4 g = reinterpret_cast<const float4*>(t.acc)[i];
+        g.x += gn.x; g.y += gn.y; g.z += gn.z; g.w += gn.w;
+        reinterpret_cast<float4*>(t.acc)[i] = g;
+        float4 p = reinterpret_cast<float4*>(t.p)[i], m = reinterpret_cast<float4*>(t.m)[i];
+        float4 v = reinterpret_cast<float4*>(t.v)[i], vm = reinterpret_cast<float4*>(t.vmax)[i];
+        update(g.x, p.x, m.x, v.x, vm.x);
+        update(g.y, p.y, m.y, v.y, vm.y);
+        update(g.z, p.z, m.z, v.z, vm.z);
+        update(g.w, p.w, m.w, v.w, vm.w);
+        reinterpret_cast<float4*>(t.m)[i] = m;
+        reinterpret_cast<float4*>(t.v)[i] = v;
+        reinterpret_cast<float4*>(t.vmax)[i] = vm;
+        if (MC) {
+            mc_st(map.param_mc + e, p);
+        } else {
+            for (int k = 0; k < map.world; ++k) peer_st(map.param[k] + e, p);
+        }
+    }
+}
+
 }  // namespace c2dsr
 
 using namespace c2dsr;
@@ -315,6 +403,29 @@ int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64
         table_dev, lr, beta1, beta2, eps, weight_decay, (float)(1.0 / bc1), (float)sqrt(bc2), nullptr);
     note_launches(1);
     return check_launch("adamw_amsgrad");
+}
+
+int c2dsr_adamw_amsgrad_peer(const c2dsr_peer_tensor* table_dev, int n_tensors, int64_t max_n,
+                             const c2dsr_peer_map* map, const void* state, float beta1, float beta2, float eps,
+                             float weight_decay, void* stream) {
+    if (n_tensors <= 0) return C2DSR_OK;
+    C2DSR_REQUIRE(state != nullptr && map != nullptr, "state and map must not be NULL");
+    C2DSR_REQUIRE(map->world >= 1 && map->world <= C2DSR_MAX_PEERS && map->rank >= 0 && map->rank < map->world,
+                  "bad peer map");
+    C2DSR_REQUIRE(max_n % 4 == 0, "slices must be multiples of 4 elements");
+    int64_t chunks = ceil_div(max_n, 256 * 4);
+    if (chunks > 148 * 8) chunks = 148 * 8;
+    if (chunks < 1) chunks = 1;
+    const dim3 grid((unsigned)chunks, (unsigned)n_tensors);
+    const auto* st = reinterpret_cast<const c2dsr_step_state*>(state);
+    if (map->grad_mc != nullptr && map->param_mc != nullptr)
+        adamw_peer_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, *map, beta1, beta2, eps,
+                                                                       weight_decay, st);
+    else
+        adamw_peer_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, *map, beta1, beta2, eps,
+                                                                        weight_decay, st);
+    note_launches(1);
+    return check_launch("adamw_amsgrad_peer");
 }
 
 }  // extern "C"

@@ -111,12 +111,27 @@ class FlatShards:
     def param_shard(self) -> torch.Tensor:
         return self.flat[self.rank * self.shard:(self.rank + 1) * self.shard]
 
-    def reduce_scatter_grads(self) -> torch.Tensor:
-        """bucket <- this step's gradients; grad_shard <- sum over ranks of bucket[shard of this rank]."""
+    def rebase(self, flat: torch.Tensor, bucket: torch.Tensor):
+        """Move the flat parameter buffer and the gradient bucket into caller-supplied storage of the same size
+        (the symmetric block of the peer-memory step)."""
+        with torch.no_grad():
+            flat.copy_(self.flat)
+            bucket.zero_()
+            self.flat, self.bucket = flat, bucket
+            for p, off in zip(self.params, self.offsets):
+                p.data = self.flat[off:off + p.numel()].view_as(p)
+        self.views = [self.bucket[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+
+    def stage_grads(self):
+        """bucket <- this step's gradients."""
         # a parameter of the frozen layout that got no gradient this step (e.g. a classifier whose domain has no
         # valid row in this rank's shard) contributes zeros -- never a missing collective operand
         torch._foreach_copy_(self.views, [p.grad if p.grad is not None else torch.zeros_like(v)
                                           for p, v in zip(self.params, self.views)])
+
+    def reduce_scatter_grads(self) -> torch.Tensor:
+        """bucket <- this step's gradients; grad_shard <- sum over ranks of bucket[shard of this rank]."""
+        self.stage_grads()
         if dist.get_backend() == "gloo":                     # CPU tests: gloo has no reduce-scatter
             dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM)
             self.grad_shard.copy_(self.bucket[self.rank * self.shard:(self.rank + 1) * self.shard])
@@ -155,6 +170,7 @@ class ShardedStep:
         from ._cabi import AdamTensor, ptr
         self.rank, self.world_size, self.opt = rank, world_size, optimizer
         params = list(params)
+        early_ids = {id(p) for p in early}
         self.big = []
         small = []
         for p in params:
@@ -163,7 +179,7 @@ class ShardedStep:
                 flat = p.data.view(-1)
                 z = lambda: torch.zeros(per, dtype=torch.float32, device=p.device)
                 st = dict(p=p, per=per, flat=flat, pshard=flat[rank * per:(rank + 1) * per], gshard=z(), m=z(), v=z(),
-                          vmax=z(), gsum=z(), done=False, idx=len(self.big))
+                          vmax=z(), gsum=z(), done=False, idx=len(self.big), early=id(p) in early_ids)
                 host = (AdamTensor * 1)()
                 host[0].p, host[0].g, host[0].acc = ptr(st["pshard"]), ptr(st["gshard"]), ptr(st["gsum"])
                 host[0].m, host[0].v, host[0].vmax = ptr(st["m"]), ptr(st["v"]), ptr(st["vmax"])
@@ -173,6 +189,9 @@ class ShardedStep:
             else:
                 small.append(p)
         self.small = FlatShards(small, rank, world_size) if small else None
+        self.peer = self.small_peer = None
+        if self.big and self.big[0]["p"].is_cuda and os.environ.get("C2DSR_DP", "peer") != "nccl":
+            self._setup_peer()
         self.streams = tuple(torch.cuda.Stream() for _ in self.big)
         self._used = set()
         self.params = params
@@ -181,6 +200,109 @@ class ShardedStep:
         for st in self.big:
             if id(st["p"]) in early:
                 self._hooks.append(st["p"].register_post_accumulate_grad_hook(lambda p, st=st: self._pipeline(st)))
+
+    # ---- peer-memory path: gradient all-reduce + AdamW + parameter broadcast as ONE kernel over NVLink -------
+    def _setup_peer(self):
+        """Move the large tensors into one symmetric block per rank ([parameters | gradients], peer-mapped into
+        every process and, where the NVSwitch offers it, bound to a multicast address) and build the tables of
+        ``c2dsr_adamw_amsgrad_peer``.  The backward writes those gradients straight into the gradient half
+        (``ops.GRAD_SINKS``).  Any failure to set this up -- no P2P mapping between the GPUs, a torch build without
+        symmetric memory -- is agreed on by all ranks and leaves the NCCL pipeline in place."""
+        from . import ops
+        from ._cabi import PeerMap, PeerTensor, ptr
+        dev = self.big[0]["p"].device
+        n_small = self.small.shard * self.world_size if self.small is not None else 0
+        total = sum(st["p"].numel() for st in self.big) + n_small
+        ok = torch.ones(1, device=dev)
+        block = hdl = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            block = symm.empty(2 * total, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(block, dist.group.WORLD)
+            if len(hdl.buffer_ptrs) != self.world_size:
+                raise RuntimeError("symmetric memory: peer pointers missing")
+        except Exception as e:                                   # noqa: BLE001 -- every failure means "use NCCL"
+            ok.zero_()
+            self.peer_error = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            return
+        block.zero_()
+        # multicast moves (1 + 1 / world) x the bytes per NVLink direction (every copy, the local one included,
+        # passes the switch), plain peer loads / stores 2 (world - 1) / world x: multicast from 4 ranks on
+        mode = os.environ.get("C2DSR_DP", "peer")
+        want_mc = mode == "multimem" or (mode != "p2p" and self.world_size >= 4)
+        mc = int(hdl.multicast_ptr) if want_mc and getattr(hdl, "has_multicast_support", False) else 0
+        pmap = PeerMap()
+        pmap.world, pmap.rank = self.world_size, self.rank
+        for k in range(self.world_size):
+            pmap.param[k] = int(hdl.buffer_ptrs[k])
+            pmap.grad[k] = int(hdl.buffer_ptrs[k]) + 4 * total
+        pmap.param_mc = mc or None
+        pmap.grad_mc = (mc + 4 * total) if mc else None
+        off = 0
+        with torch.no_grad():
+            for st in self.big:
+                p, n, per = st["p"], st["p"].numel(), st["per"]
+                view = block[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                st["flat"] = p.data.view(-1)
+                st["pshard"] = st["flat"][self.rank * per:(self.rank + 1) * per]
+                st["sink"] = block[total + off:total + off + n].view_as(p)
+                ops.GRAD_SINKS[p.data_ptr()] = st["sink"]
+                if not st["early"]:
+                    ops.GRAD_READY[p.data_ptr()] = lambda st=st: self._pipeline(st, staged=True)
+                host = (PeerTensor * 1)()
+                host[0].t.p, host[0].t.g, host[0].t.acc = ptr(st["pshard"]), None, ptr(st["gsum"])
+                host[0].t.m, host[0].t.v, host[0].t.vmax = ptr(st["m"]), ptr(st["v"]), ptr(st["vmax"])
+                host[0].t.n = per
+                host[0].offset = off + self.rank * per
+                st["peer_entry"] = bytes(host)
+                st["peer_table"] = torch.frombuffer(bytearray(st["peer_entry"]), dtype=torch.uint8).to(dev)
+                off += n
+            if self.small is not None:
+                # the small tensors' flat buffer and gradient bucket move into the block as one more "tensor"
+                self.small.rebase(block[off:off + n_small], block[total + off:total + off + n_small])
+                per = self.small.shard
+                z = lambda: torch.zeros(per, dtype=torch.float32, device=dev)
+                sp = dict(p=None, per=per, pshard=self.small.param_shard, gsum=z(), m=z(), v=z(), vmax=z(),
+                          done=False, idx=len(self.big), early=False)
+                host = (PeerTensor * 1)()
+                host[0].t.p, host[0].t.g, host[0].t.acc = ptr(sp["pshard"]), None, ptr(sp["gsum"])
+                host[0].t.m, host[0].t.v, host[0].t.vmax = ptr(sp["m"]), ptr(sp["v"]), ptr(sp["vmax"])
+                host[0].t.n = per
+                host[0].offset = off + self.rank * per
+                sp["peer_entry"] = bytes(host)
+                self.small_peer = sp
+        self.peer = dict(block=block, hdl=hdl, map=pmap, total=total, multicast=bool(mc), tables={}, device=dev)
+        hdl.barrier(channel=0)
+
+    def _peer_barrier(self, channel: int):
+        self.peer["hdl"].barrier(channel=channel, timeout_ms=60000)
+
+    def _peer_stage(self, st):
+        """The gradient of one tensor into the symmetric block (a no-op when the backward wrote it there)."""
+        g = st["p"].grad
+        if g is None:
+            st["sink"].zero_()
+        elif g.data_ptr() != st["sink"].data_ptr():
+            st["sink"].copy_(g)
+
+    def _peer_update(self, sts, stream):
+        """Gradients of ``sts`` complete on every rank -> one launch: all-reduce + AdamW + broadcast of the slices."""
+        import ctypes as C
+        from ._cabi import call, ptr
+        key = tuple(st["idx"] for st in sts)
+        table = self.peer["tables"].get(key)
+        if table is None:
+            raw = b"".join(st["peer_entry"] for st in sts)
+            table = self.peer["tables"][key] = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(
+                self.peer["device"])
+        group = self.opt.param_groups[0]
+        b1, b2 = group["betas"]
+        call("c2dsr_adamw_amsgrad_peer", ptr(table), len(sts), max(st["per"] for st in sts), C.addressof(self.peer["map"]),
+             ptr(self.opt.dyn_state), b1, b2, group["eps"], group["weight_decay"], stream.cuda_stream)
 
     def _stream_of(self, st):
         idx = st["idx"]
@@ -211,11 +333,21 @@ class ShardedStep:
             dist.all_gather_into_tensor(st["flat"], st["pshard"])
         st["done"] = True
 
-    def _pipeline(self, st):
-        """The whole update of one tensor (post-accumulate-grad hook of the classifier matrices)."""
+    def _pipeline(self, st, staged: bool = False):
+        """The whole update of one tensor, started as soon as its gradient is complete: from the post-accumulate-
+        grad hook of a classifier matrix, or (``staged``: the gradient already sits in the symmetric block) from
+        the backward of an embedding table's branch."""
         if st["done"]:
             return
         stream = self._stream_of(st)
+        if self.peer is not None:
+            with torch.cuda.stream(stream):
+                if not staged:
+                    self._peer_stage(st)
+                self._peer_barrier(1 + st["idx"])            # every rank's gradient of this tensor is in place
+                self._peer_update([st], stream)
+            st["done"] = True
+            return
         self._reduce(st, stream)
         self._update(st, stream)
         self._gather(st, stream)
@@ -226,27 +358,60 @@ class ShardedStep:
         reduce-scatters are launched first (a collective kernel takes a few dozen CTAs), then the AdamW slices --
         each starts when its own reduce-scatter is done and runs beside the later ones -- then the all-gathers; last
         the small-tensor bucket on the caller's stream, and the join of the communication streams."""
-        todo = [(st, self._stream_of(st)) for st in self.big if not st["done"]]
-        for st, stream in todo:
-            self._reduce(st, stream)
-        for st, stream in todo:
-            self._update(st, stream)
-        for st, stream in todo:
-            self._gather(st, stream)
-        if self.small is not None:
+        cur = torch.cuda.current_stream()
+        if self.peer is not None:
+            # the embedding tables, together, on the caller's stream: one barrier, one launch over their slices;
+            # the small-tensor bucket (NCCL) meanwhile; one last barrier once every stream has joined -- after
+            # it all parameter blocks are complete and all gradient blocks may be overwritten
+            todo = [st for st in self.big if not st["done"]]
+            for st in todo:
+                self._peer_stage(st)
+            if self.small is not None:
+                self.small.stage_grads()
+                todo.append(self.small_peer)
+            if todo:
+                self._peer_barrier(0)
+                self._peer_update(todo, cur)
+            self.opt.n_steps += 1
+            if not torch.cuda.is_current_stream_capturing():
+                self.opt.sync_lr()
+        else:
+            todo = [(st, self._stream_of(st)) for st in self.big if not st["done"]]
+            for st, stream in todo:
+                self._reduce(st, stream)
+            for st, stream in todo:
+                self._update(st, stream)
+            for st, stream in todo:
+                self._gather(st, stream)
+        if self.peer is not None:
+            pass
+        elif self.small is not None:
             self.opt.step_flat(self.small.param_shard, self.small.reduce_scatter_grads())
             self.small.all_gather_params()
         else:
             self.opt.n_steps += 1
-        cur = torch.cuda.current_stream()
         for i in sorted(self._used):                  # (only streams that carry work of this step: capture-safe)
             cur.wait_stream(self.streams[i])
         self._used.clear()
+        if self.peer is not None:
+            self._peer_barrier(1 + len(self.big))
         for st in self.big:
             st["done"] = False
         for p in self.params:
             p.grad = None
 
+    def close(self):
+        """Forget the gradient sinks / hooks registered for this step's tensors (before the object is dropped)."""
+        from . import ops
+        for st in self.big:
+            ops.GRAD_SINKS.pop(st["p"].data_ptr(), None)
+            ops.GRAD_READY.pop(st["p"].data_ptr(), None)
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
     def zero_grad_sums(self):
         for st in self.big:
             st["gsum"].zero_()
+        if self.small_peer is not None:
+            self.small_peer["gsum"].zero_()

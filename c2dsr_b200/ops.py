@@ -17,6 +17,20 @@ F32, I64, I32 = torch.float32, torch.int64, torch.int32
 LN_EPS = 1e-8          # models/encoders.py:24-27 of the reference
 
 
+# parameter storage address -> tensor its gradient should be written into (data-parallel training over peer
+# memory: the gradient block every rank can read, dist.ShardedStep._setup_peer).  Empty otherwise.
+GRAD_SINKS = {}
+# parameter storage address -> callable run (on the producing stream) as soon as that sink holds the complete
+# gradient of the step: lets the optimiser pipeline of an embedding table start inside the backward
+GRAD_READY = {}
+
+
+def grad_sink(param_ptr):
+    """A fresh alias of the registered sink (autograd may then adopt it as ``.grad`` without a copy), or None."""
+    t = GRAD_SINKS.get(param_ptr)
+    return None if t is None else t.view_as(t)
+
+
 def _f(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == F32 else t.float().contiguous()
 
@@ -82,20 +96,20 @@ def gcn_forward(E, g, n_gnn: int, p: float, seed: int, tag: int, need=None):
 
 
 def gcn_backward(g, d_hi, k: int, p: float, seed: int, tag: int, direct: bool = False, pad_idx: int = -1,
-                 nz=None):
+                 nz=None, out=None):
     """Gradient w.r.t. E of hi = GCN(E) (k >= 1 hops) given d_hi:  g_k = c d_hi,  g_{j-1} = c d_hi + m_j .* (A^T g_j).
     ``direct=True`` folds in the gradient of the branch's direct look-up E[seq] as well, which equals d_hi on every
     row except the pad row (``nn.Embedding(padding_idx)`` blocks it there): the last product then uses
     beta = c + 1 and the pad row is corrected, so neither a second dense [N, d] gradient nor the add of the two
     is ever materialised.  ``nz`` (uint8 row mask): rows of d_hi outside it are exactly zero (items the batch
-    did not touch) and the first product skips them."""
+    did not touch) and the first product skips them.  ``out``: where the last product writes the gradient."""
     c = 1.0 / (k + 1)
     extra = 1.0 if direct else 0.0
     cur = spmm(g.bwd, d_hi, Y=d_hi, alpha=c, beta=c + (extra if k == 1 else 0.0), drop_mode=2, p=p, seed=seed,
-               tag=tag * 16 + k, x_nz=nz)
+               tag=tag * 16 + k, x_nz=nz, out=out if k == 1 else None)
     for j in range(k - 1, 0, -1):
         cur = spmm(g.bwd, cur, Y=d_hi, alpha=1.0, beta=c + (extra if j == 1 else 0.0), drop_mode=2, p=p, seed=seed,
-                   tag=tag * 16 + j)
+                   tag=tag * 16 + j, out=out if j == 1 else None)
     if direct:
         cur[pad_idx].sub_(d_hi[pad_idx])
     return cur
@@ -348,7 +362,10 @@ class BranchSetFn(torch.autograd.Function):
                 if gcn is not None:
                     graph, k, gp, gseed, gtag = gcn
                     d_E = gcn_backward(graph, d_hi, k, gp, gseed, gtag, direct=True, pad_idx=sp["pad"],
-                                       nz=mark_rows(seq, hi_shape[0]))
+                                       nz=mark_rows(seq, hi_shape[0]), out=grad_sink(sp.get("table_ptr")))
+                    ready = GRAD_READY.get(sp.get("table_ptr"))
+                    if ready is not None:
+                        ready()
                     d_hi = None
             result[i] = [d_hi, d_E, d_P, *grads]
         for st in streams:
@@ -562,7 +579,8 @@ class DomainLossTcFn(torch.autograd.Function):
         N = W.shape[0]
         dev = h_share.device
         dH = torch.empty(M, d, device=dev, dtype=F32)
-        dW = torch.zeros(N, d, device=dev, dtype=F32)
+        dW = grad_sink(W.data_ptr())
+        dW = torch.zeros(N, d, device=dev, dtype=F32) if dW is None else dW.zero_()
         db = torch.zeros(N, device=dev, dtype=F32)
         dzpad = torch.empty(M, device=dev, dtype=F32)
         if M > 0:

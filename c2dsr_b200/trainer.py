@@ -247,6 +247,11 @@ class Trainer(object):
                     [m.classifier_a.weight, m.classifier_b.weight]
                 self.shards = cdist.ShardedStep(live, self.rank, self.world_size, self.optimizer, early=early)
                 self.optimizer.sharded = self.shards
+                # the parameters now live in the step's flat / symmetric buffers: nothing captured or cached
+                # against their old storage may be replayed
+                self._wsplit.clear()
+                self._eval_graph = None
+                self.model._pad_cache = {}
             self.shards.finish()
             call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
             out = torch.stack((loss.detach(), loss_rec.detach(), loss_mi.detach()))

@@ -344,6 +344,31 @@ int c2dsr_step_begin(void* state, uint64_t seed_base, void* stream);
 int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, const void* state,
                             float beta1, float beta2, float eps, float weight_decay, void* stream);
 
+/* Data-parallel form of the same update over peer memory (NVLink / NVSwitch), one launch: the gradients of the large
+ * tensors live at the same offsets of a "gradient block" on every rank, the parameters of a "parameter block"; all
+ * blocks are peer-mapped into every process (map.grad[k], map.param[k] = rank k's blocks as seen from this process;
+ * map.grad_mc / map.param_mc = multicast addresses of the blocks, or NULL).  For each tensor of the table this rank
+ * updates its own slice: gradient = sum over ranks of grad[k][offset + i] (multimem.ld_reduce when the multicast
+ * addresses are given, else peer loads in rank order), AdamW-amsgrad as above on t.p / t.acc / t.m / t.v / t.vmax
+ * (t.p = this rank's slice inside its own parameter block, t.g ignored, t.n % 4 == 0), and the new values are
+ * stored into every rank's parameter block (multimem.st / peer stores).  The caller brackets the launch with
+ * barriers over all ranks: gradients complete before, nobody reads parameters until after. */
+#define C2DSR_MAX_PEERS 16
+typedef struct {
+    c2dsr_adam_tensor t;
+    int64_t offset;
+} c2dsr_peer_tensor;
+typedef struct {
+    int world, rank;
+    const float* grad[C2DSR_MAX_PEERS];
+    float* param[C2DSR_MAX_PEERS];
+    const float* grad_mc;
+    float* param_mc;
+} c2dsr_peer_map;
+int c2dsr_adamw_amsgrad_peer(const c2dsr_peer_tensor* table_dev, int n_tensors, int64_t max_n,
+                             const c2dsr_peer_map* map, const void* state, float beta1, float beta2, float eps,
+                             float weight_decay, void* stream);
+
 /* elementwise glue: out = a*x + b*y (y may be NULL) */
 int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);
 

@@ -36,7 +36,7 @@ if rank == 0:
     last = [e for e in evs if e.time_range.start >= t_first + span * (N - 1) - 5]
     t0 = last[0].time_range.start
     for e in last:
-        if e.device_time >= 15 or "nccl" in e.name.lower():
+        if e.device_time >= 15 or "nccl" in e.name.lower() or "barrier" in e.name.lower() or "peer" in e.name.lower():
             print(f"S{getattr(e, 'device_resource_id', 0):<4d} {e.time_range.start - t0:8.1f} {e.device_time:7.1f}  {e.name[:80]}")
 import gc
 tr._graphs.clear(); gc.collect(); torch.cuda.synchronize()
