@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor
         p -= step_size * (m / (sqrtf(vm) / sqrt_bc2 + eps));
     };
     const int64_t n4 = t.n >> 2;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    auto fetch = [&](int64_t i) {                      // the gradient of elements 4 i .. 4 i + 3, summed over the ranks
         const int64_t e = job.offset + i * 4;
         float4 gn;
         if (MC) {
@@ -285,6 +285,10 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor
                 gn.x += x.x; gn.y += x.y; gn.z += x.z; gn.w += x.w;
             }
         }
+        return gn;
+    };
+    auto apply = [&](int64_t i, float4 gn) {
+        const int64_t e = job.offset + i * 4;
         float4 g = reinterpret_cast<const float4*>(t.acc)[i];
         g.x += gn.x; g.y += gn.y; g.z += gn.z; g.w += gn.w;
         reinterpret_cast<float4*>(t.acc)[i] = g;
@@ -302,7 +306,17 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor
         } else {
             for (int k = 0; k < map.world; ++k) peer_st(map.param[k] + e, p);
         }
+    };
+    // four remote fetches in flight per thread before the first is consumed (NVLink round trips are microseconds)
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 g0 = fetch(i), g1 = fetch(i + stride), g2 = fetch(i + 2 * stride), g3 = fetch(i + 3 * stride);
+        apply(i, g0);
+        apply(i + stride, g1);
+        apply(i + 2 * stride, g2);
+        apply(i + 3 * stride, g3);
     }
+    for (; i < n4; i += stride) apply(i, fetch(i));
 }
 
 }  // namespace c2dsr

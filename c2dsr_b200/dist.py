@@ -33,6 +33,9 @@ def init_from_env(backend: str = "nccl") -> Tuple[int, int, int]:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world_size > 1 and not dist.is_initialized():
+        # the data-parallel step runs ~10 streams side by side (branches, per-tensor optimiser pipelines with
+        # cross-rank barriers): give every stream a hardware queue of its own (read when the CUDA context is made)
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         if backend == "nccl":
@@ -228,10 +231,11 @@ class ShardedStep:
         if ok.item() == 0:
             return
         block.zero_()
-        # multicast moves (1 + 1 / world) x the bytes per NVLink direction (every copy, the local one included,
-        # passes the switch), plain peer loads / stores 2 (world - 1) / world x: multicast from 4 ranks on
-        mode = os.environ.get("C2DSR_DP", "peer")
-        want_mc = mode == "multimem" or (mode != "p2p" and self.world_size >= 4)
+        # multicast (multimem.ld_reduce / multimem.st, C2DSR_DP=multimem) moves (1 + 1 / world) x the bytes per
+        # NVLink direction, plain peer loads / stores 2 (world - 1) / world x -- yet measured on 2 and 4 B200s the
+        # peer loads / stores are faster (4 GPUs: 3.36 vs 3.47 ms per step), and they sum in rank order, so the
+        # result does not depend on the switch: they are the default
+        want_mc = os.environ.get("C2DSR_DP", "peer") == "multimem"
         mc = int(hdl.multicast_ptr) if want_mc and getattr(hdl, "has_multicast_support", False) else 0
         pmap = PeerMap()
         pmap.world, pmap.rank = self.world_size, self.rank
