@@ -475,8 +475,10 @@ def run_b200(a):
                           "achieved": round(alg / t / 1e6, 1), "peak": pk["hbm"], "unit": "GB/s",
                           "frac": round(alg / t / 1e6 / pk["hbm"], 4)})
         model.train()
+        tr.optimizer.early_enabled = False        # (timed on its own: the whole update at the end of the backward)
         per = profiled({"c2dsr_gather_fwd", "c2dsr_gather_bwd", "c2dsr_adamw_amsgrad_dyn", "c2dsr_adamw_amsgrad"},
                        lambda: [(model.convolve_graph(lazy=True), tr.train_batch(dev_tb[i % len(dev_tb)])) for i in range(3)])
+        tr.optimizer.early_enabled = True
         T_step = 5 * B * L
         gf = sum(per.get("c2dsr_gather_fwd", [0.0])) / 3
         gb = sum(per.get("c2dsr_gather_bwd", [0.0])) / 3

@@ -111,10 +111,10 @@ _PROTOS = {
     "c2dsr_step_state_set": (i32, [vp, i64, f32, vp]),
     "c2dsr_step_state_set_lr": (i32, [vp, f32, vp]),
     "c2dsr_step_begin": (i32, [vp, u64, vp]),
-    "c2dsr_adamw_amsgrad_dyn": (i32, [vp, i32, i64, vp, f32, f32, f32, f32, vp]),
+    "c2dsr_adamw_amsgrad_dyn": (i32, [vp, i32, i64, vp, f32, f32, f32, f32, i32, vp]),
     "c2dsr_preprocess_train": (i32, [vp, vp, vp, i64, i64, i64, i32, vp, vp, vp]),
     "c2dsr_preprocess_eval": (i32, [vp, vp, i64, i64, i64, i32, i32, vp, vp, vp, vp]),
-    "c2dsr_adamw_amsgrad_peer": (i32, [vp, i32, i64, vp, vp, f32, f32, f32, f32, vp]),
+    "c2dsr_adamw_amsgrad_peer": (i32, [vp, i32, i64, vp, vp, f32, f32, f32, f32, i32, vp]),
     "c2dsr_axpby": (i32, [vp, vp, vp, i64, f32, f32, vp]),
 }
 EXPORTS = tuple(_PROTOS)

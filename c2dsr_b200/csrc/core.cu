@@ -392,13 +392,21 @@ int c2dsr_step_begin(void* state, uint64_t seed_base, void* stream) {
     return check_launch("step_begin");
 }
 
+// background != 0: the launch runs beside higher-priority work (early optimiser steps): one short-lived CTA per
+// 1 024 (4 096 for the peer kernel) elements instead of a resident grid-stride grid, so that the SMs are handed
+// back to the step's own chain whenever it has a kernel to place
+static int64_t adam_chunks(int64_t max_n, int64_t per_cta, int background) {
+    int64_t chunks = ceil_div(max_n, per_cta);
+    if (!background && chunks > 148 * 8) chunks = 148 * 8;
+    if (chunks > 0x7fffffff) chunks = 0x7fffffff;
+    return chunks < 1 ? 1 : chunks;
+}
+
 int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, const void* state,
-                            float beta1, float beta2, float eps, float weight_decay, void* stream) {
+                            float beta1, float beta2, float eps, float weight_decay, int background, void* stream) {
     if (n_tensors <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(state != nullptr, "state must not be NULL");
-    int64_t chunks = ceil_div(max_n, 256 * 4);
-    if (chunks > 148 * 8) chunks = 148 * 8;
-    if (chunks < 1) chunks = 1;
+    const int64_t chunks = adam_chunks(max_n, 256 * 4, background);
     adamw_kernel<<<dim3((unsigned)chunks, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(
         table_dev, 0.f, beta1, beta2, eps, weight_decay, 0.f, 0.f, reinterpret_cast<const c2dsr_step_state*>(state));
     note_launches(1);
@@ -421,15 +429,13 @@ int c2dsr_adamw_amsgrad(const c2dsr_adam_tensor* table_dev, int n_tensors, int64
 
 int c2dsr_adamw_amsgrad_peer(const c2dsr_peer_tensor* table_dev, int n_tensors, int64_t max_n,
                              const c2dsr_peer_map* map, const void* state, float beta1, float beta2, float eps,
-                             float weight_decay, void* stream) {
+                             float weight_decay, int background, void* stream) {
     if (n_tensors <= 0) return C2DSR_OK;
     C2DSR_REQUIRE(state != nullptr && map != nullptr, "state and map must not be NULL");
     C2DSR_REQUIRE(map->world >= 1 && map->world <= C2DSR_MAX_PEERS && map->rank >= 0 && map->rank < map->world,
                   "bad peer map");
     C2DSR_REQUIRE(max_n % 4 == 0, "slices must be multiples of 4 elements");
-    int64_t chunks = ceil_div(max_n, 256 * 4);
-    if (chunks > 148 * 8) chunks = 148 * 8;
-    if (chunks < 1) chunks = 1;
+    const int64_t chunks = adam_chunks(max_n, background ? 256 * 16 : 256 * 4, background);
     const dim3 grid((unsigned)chunks, (unsigned)n_tensors);
     const auto* st = reinterpret_cast<const c2dsr_step_state*>(state);
     if (map->grad_mc != nullptr && map->param_mc != nullptr)

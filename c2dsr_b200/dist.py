@@ -14,6 +14,7 @@ box, gloo in the CPU tests).  The path has exactly two exchange steps (SURVEY.md
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Tuple
 
 import torch
@@ -256,7 +257,8 @@ class ShardedStep:
                 st["sink"] = block[total + off:total + off + n].view_as(p)
                 ops.GRAD_SINKS[p.data_ptr()] = st["sink"]
                 if not st["early"]:
-                    ops.GRAD_READY[p.data_ptr()] = lambda st=st: self._pipeline(st, staged=True)
+                    me = weakref.ref(self)
+                    ops.GRAD_READY[p.data_ptr()] = lambda st=st, me=me: me() is not None and me()._pipeline(st, staged=True)
                 host = (PeerTensor * 1)()
                 host[0].t.p, host[0].t.g, host[0].t.acc = ptr(st["pshard"]), None, ptr(st["gsum"])
                 host[0].t.m, host[0].t.v, host[0].t.vmax = ptr(st["m"]), ptr(st["v"]), ptr(st["vmax"])
@@ -280,6 +282,7 @@ class ShardedStep:
                 sp["peer_entry"] = bytes(host)
                 self.small_peer = sp
         self.peer = dict(block=block, hdl=hdl, map=pmap, total=total, multicast=bool(mc), tables={}, device=dev)
+        weakref.finalize(self, ops.forget_grad_hooks, [st["p"].data_ptr() for st in self.big])
         hdl.barrier(channel=0)
 
     def _peer_barrier(self, channel: int):
@@ -293,7 +296,7 @@ class ShardedStep:
         elif g.data_ptr() != st["sink"].data_ptr():
             st["sink"].copy_(g)
 
-    def _peer_update(self, sts, stream):
+    def _peer_update(self, sts, stream, background: bool = False):
         """Gradients of ``sts`` complete on every rank -> one launch: all-reduce + AdamW + broadcast of the slices."""
         import ctypes as C
         from ._cabi import call, ptr
@@ -306,7 +309,7 @@ class ShardedStep:
         group = self.opt.param_groups[0]
         b1, b2 = group["betas"]
         call("c2dsr_adamw_amsgrad_peer", ptr(table), len(sts), max(st["per"] for st in sts), C.addressof(self.peer["map"]),
-             ptr(self.opt.dyn_state), b1, b2, group["eps"], group["weight_decay"], stream.cuda_stream)
+             ptr(self.opt.dyn_state), b1, b2, group["eps"], group["weight_decay"], int(background), stream.cuda_stream)
 
     def _stream_of(self, st):
         idx = st["idx"]
@@ -330,7 +333,7 @@ class ShardedStep:
         b1, b2 = group["betas"]
         with torch.cuda.stream(stream):
             call("c2dsr_adamw_amsgrad_dyn", ptr(st["table"]), 1, st["per"], ptr(self.opt.dyn_state), b1, b2, group["eps"],
-                 group["weight_decay"], stream.cuda_stream)
+                 group["weight_decay"], 0, stream.cuda_stream)
 
     def _gather(self, st, stream):
         with torch.cuda.stream(stream):
@@ -349,7 +352,7 @@ class ShardedStep:
                 if not staged:
                     self._peer_stage(st)
                 self._peer_barrier(1 + st["idx"])            # every rank's gradient of this tensor is in place
-                self._peer_update([st], stream)
+                self._peer_update([st], stream, background=True)
             st["done"] = True
             return
         self._reduce(st, stream)

@@ -51,6 +51,9 @@ FLAGS = [
     ("--skip_ignored_rows", dict(type=int, default=1, help="0: run the loss GEMMs on ignore_index rows too")),
     ("--cuda_graph", dict(type=int, default=1, help="0: launch every kernel of a training step eagerly")),
     ("--device_graph", dict(action="store_true", help="with --use_raw: build the adjacency CSRs on the GPU")),
+    ("--early_adam", dict(type=int, default=1,
+                          help="0: one GPU: update every tensor at the end of the backward (1: large tensors as soon as "
+                               "their gradient is complete, beside the rest of the backward)")),
     ("--device_preprocess", dict(action="store_true",
                                  help="with --use_raw: derive the splits' fields on the GPU (random draws stay on the "
                                       "host, in the reference's order)")),

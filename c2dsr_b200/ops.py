@@ -25,10 +25,22 @@ GRAD_SINKS = {}
 GRAD_READY = {}
 
 
+# Sinks and ready-callbacks assume that the parameter receives exactly ONE gradient contribution in the backward:
+# true for the Trainer's own step (forward_all: one branch per table; one loss node per classifier), which arms them
+# around its ``loss.backward()``.  Any other backward (model API used directly, tests) never sees them.
+ARMED = [False]
+
+
 def grad_sink(param_ptr):
     """A fresh alias of the registered sink (autograd may then adopt it as ``.grad`` without a copy), or None."""
-    t = GRAD_SINKS.get(param_ptr)
+    t = GRAD_SINKS.get(param_ptr) if ARMED[0] else None
     return None if t is None else t.view_as(t)
+
+
+def forget_grad_hooks(ptrs):
+    for q in ptrs:
+        GRAD_SINKS.pop(q, None)
+        GRAD_READY.pop(q, None)
 
 
 def _f(t: torch.Tensor) -> torch.Tensor:
@@ -361,9 +373,12 @@ class BranchSetFn(torch.autograd.Function):
                 del dx
                 if gcn is not None:
                     graph, k, gp, gseed, gtag = gcn
+                    # (sink / early step only for a table that a single branch of this step reads)
+                    tp = sp.get("table_ptr")
+                    single = tp is not None and sum(1 for s in specs if s.get("table_ptr") == tp) == 1
                     d_E = gcn_backward(graph, d_hi, k, gp, gseed, gtag, direct=True, pad_idx=sp["pad"],
-                                       nz=mark_rows(seq, hi_shape[0]), out=grad_sink(sp.get("table_ptr")))
-                    ready = GRAD_READY.get(sp.get("table_ptr"))
+                                       nz=mark_rows(seq, hi_shape[0]), out=grad_sink(tp) if single else None)
+                    ready = GRAD_READY.get(tp) if (ARMED[0] and single) else None
                     if ready is not None:
                         ready()
                     d_hi = None

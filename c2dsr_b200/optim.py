@@ -37,11 +37,75 @@ class FusedAdamW(torch.optim.Optimizer):
         self._table_dev = None
         self._graph_tables = []   # pinned tables referenced by captured memcpy nodes: must outlive the graphs
         self.n_steps = 0          # bumped on every step(): parameters are updated through raw pointers
+        self.early_enabled = True # (enable_early: set False to run every update at the end of the backward)
         # device-resident step state (c2dsr_step_state, see the header): when attached, the step number and the
         # learning rate are read by the kernel itself, which is what lets a whole training step be replayed
         # from a CUDA graph.  The caller advances it with c2dsr_step_begin after every step.
         self.dyn_state = None
         self._dyn_lr = None
+
+    # ---- early steps: update a tensor the moment its gradient is complete, beside the rest of the backward ----
+    def enable_early(self, hooked=(), staged=()):
+        """The update is HBM-bound (48 B per parameter) while the encoder / gather backward that follows the K4a
+        backward is latency-bound: the large tensors need not wait for the end of the backward.  ``hooked``:
+        parameters whose single gradient contribution is complete at their post-accumulate-grad hook (classifier
+        matrices); ``staged``: parameters whose producer announces the complete gradient itself (embedding tables:
+        ``ops.GRAD_READY``, called on the producing stream).  Each gets a persistent gradient buffer
+        (``ops.GRAD_SINKS``) the backward writes into, and its own stream; ``step()`` skips what is already done
+        and joins the streams.  Needs the device step state; only armed around the Trainer's own backward
+        (``ops.ARMED``)."""
+        import weakref
+        from . import ops
+        self._early = {}
+        self.early_enabled = True
+        me = weakref.ref(self)
+        for p in (*hooked, *staged):
+            self._early[id(p)] = dict(p=p, sink=torch.zeros_like(p), stream=torch.cuda.Stream(), done=False, key=None,
+                                      table=None)
+            ops.GRAD_SINKS[p.data_ptr()] = self._early[id(p)]["sink"]
+        self._early_hooks = [p.register_post_accumulate_grad_hook(
+            lambda q, me=me: me() is not None and ops.ARMED[0] and me()._early_step(q)) for p in hooked]
+        for p in staged:
+            ops.GRAD_READY[p.data_ptr()] = lambda p=p, me=me: me() is not None and me()._early_step(p, staged=True)
+        weakref.finalize(self, ops.forget_grad_hooks, [p.data_ptr() for p in (*hooked, *staged)])
+
+    @torch.no_grad()
+    def _early_step(self, p, staged: bool = False):
+        e = self._early.get(id(p))
+        if e is None or e["done"] or self.dyn_state is None or not self.early_enabled:
+            return
+        g = e["sink"]
+        if not staged and (p.grad is None or p.grad.data_ptr() != g.data_ptr()):
+            return                              # the gradient is not in the sink: the regular step takes it
+        capturing = torch.cuda.is_current_stream_capturing()
+        st = self.state[p]
+        if len(st) == 0:
+            if capturing:
+                return
+            st["step"] = 0
+            for k in ("exp_avg", "exp_avg_sq", "max_exp_avg_sq", "grad_sum"):
+                st[k] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        key = (p.data_ptr(),) + tuple(st[k].data_ptr() for k in ("grad_sum", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"))
+        if e["key"] != key:
+            if capturing:
+                return
+            host = (AdamTensor * 1)()
+            host[0].p, host[0].g, host[0].acc = ptr(p), ptr(g), ptr(st["grad_sum"])
+            host[0].m, host[0].v, host[0].vmax = ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), ptr(st["max_exp_avg_sq"])
+            host[0].n = p.numel()
+            e["table"] = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(p.device)
+            e["key"] = key
+        st["step"] += 1
+        group = self.param_groups[0]
+        b1, b2 = group["betas"]
+        if not capturing:
+            self.sync_lr()
+        side = e["stream"]
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            call("c2dsr_adamw_amsgrad_dyn", ptr(e["table"]), 1, p.numel(), ptr(self.dyn_state), b1, b2, group["eps"],
+                 group["weight_decay"], 1, side.cuda_stream)
+        e["done"] = True
 
     def attach_step_state(self, state: torch.Tensor):
         if len(self.param_groups) != 1:
@@ -81,7 +145,7 @@ class FusedAdamW(torch.optim.Optimizer):
             self.sync_lr()
         b1, b2 = group["betas"]
         call("c2dsr_adamw_amsgrad_dyn", ptr(st["table"]), 1, p_shard.numel(), ptr(self.dyn_state), b1, b2, group["eps"],
-             group["weight_decay"], stream())
+             group["weight_decay"], 0, stream())
 
     def accumulated_grad(self, p):
         """The gradient sum since the last zero_grad() (= ``p.grad`` of the reference); None if p never had one."""
@@ -104,9 +168,14 @@ class FusedAdamW(torch.optim.Optimizer):
     def step(self, closure=None, grads: Optional[Dict[torch.nn.Parameter, torch.Tensor]] = None):
         loss = closure() if closure is not None else None
         self.n_steps += 1
+        early = self.__dict__.get("_early") or {}
+        done = [e for e in early.values() if e["done"]]
         for gi, group in enumerate(self.param_groups):
             live = []
             for p in group["params"]:
+                e = early.get(id(p))
+                if e is not None and e["done"]:
+                    continue                    # updated already, beside the backward (enable_early)
                 g = grads.get(p) if grads is not None else p.grad
                 if g is None:
                     continue
@@ -129,6 +198,12 @@ class FusedAdamW(torch.optim.Optimizer):
             if self.accumulate:
                 for p, _, _ in live:
                     p.grad = None               # consumed: the next backward's gradient is taken over as is
+        cur = torch.cuda.current_stream() if done else None
+        for e in done:
+            cur.wait_stream(e["stream"])
+            e["done"] = False
+            if self.accumulate:
+                e["p"].grad = None
         return loss
 
     def _launch(self, gi, group, items, step_no):
@@ -174,7 +249,7 @@ class FusedAdamW(torch.optim.Optimizer):
             tab = ptr(self._table_dev) + first * C.sizeof(AdamTensor)
             if self.dyn_state is not None:
                 call("c2dsr_adamw_amsgrad_dyn", tab, count, max_n, ptr(self.dyn_state), b1, b2, group["eps"],
-                     group["weight_decay"], stream())
+                     group["weight_decay"], 0, stream())
             else:
                 call("c2dsr_adamw_amsgrad", tab, count, max_n, float(group["lr"]), b1, b2, group["eps"],
                      group["weight_decay"], step_no, stream())

@@ -89,12 +89,20 @@ class Trainer(object):
         self.seed_base = (int(getattr(args, "seed", 0)) * 0x9E3779B97F4A7C15 + 0xD1B54A32D192ED03 * (self.rank + 1)) \
             & 0xFFFFFFFFFFFFFFFF
         self.optimizer.attach_step_state(self.step_state)
+        if self.world_size == 1 and self.device.type == "cuda" and bool(getattr(args, "early_adam", True)):
+            # one GPU: the large tensors are updated beside the backward, as soon as their gradient is complete
+            # (data parallel: dist.ShardedStep does the same with its per-tensor pipelines)
+            m = self.model
+            uniq = lambda ps: list({id(p): p for p in ps if p.requires_grad}.values())
+            self.optimizer.enable_early(hooked=uniq([m.classifier_a.weight, m.classifier_b.weight]),
+                                        staged=uniq([m.embed_i.weight, m.embed_i_a.weight, m.embed_i_b.weight]))
         call("c2dsr_step_begin", ptr(self.step_state), self.seed_base, stream())
         self.model.dyn_seed = DynSeed(self.step_state.data_ptr() + 8)
         # whole-step CUDA graphs; the data-parallel step captures its NCCL all-reduces too
         self.use_graph = bool(getattr(args, "cuda_graph", True)) and \
             (self.world_size == 1 or bool(getattr(args, "cuda_graph_dp", True)))
         self._graphs, self._warm, self._caps = {}, {}, None
+        self._step_stream = None
         self._eval_graph, self._eval_seen = None, None
 
     def enable_pad_shortcut(self, eval_batches) -> bool:
@@ -236,7 +244,11 @@ class Trainer(object):
     def train_batch(self, batch):
         """trainer.py:91-160 -> (loss, loss_rec, loss_mi) as 0-d tensors (global values under DP)."""
         loss, loss_rec, loss_mi = self.losses(batch)
-        loss.backward()
+        ops.ARMED[0] = True          # one gradient contribution per table / classifier: sinks + early optimiser steps
+        try:
+            loss.backward()
+        finally:
+            ops.ARMED[0] = False
         if self.world_size > 1:
             # sharded step: reduce-scatter the gradients, update this rank's 1/world of the flat parameter
             # buffer, all-gather the parameters (dist.FlatShards)
@@ -329,8 +341,12 @@ class Trainer(object):
         graph = torch.cuda.CUDAGraph()
         l0 = _cabi.launch_count()
         self._caps = caps
+        # the step's own chain (and the model's branch streams) at high priority, the optimiser pipelines that run
+        # beside the backward at the default, lowest one: their CTAs fill what the chain leaves free
+        if self._step_stream is None:
+            self._step_stream = torch.cuda.Stream(priority=-1)
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._step_stream):
                 self.model.convolve_graph(lazy=True)
                 step_in = Batch(static)             # carries the host-side normaliser facts of the captured shape
                 step_in.global_rows = getattr(batch, "global_rows", None)

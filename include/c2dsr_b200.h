@@ -341,8 +341,10 @@ int c2dsr_step_state_bytes(void);
 int c2dsr_step_state_set(void* state, int64_t step, float lr, void* stream);
 int c2dsr_step_state_set_lr(void* state, float lr, void* stream);
 int c2dsr_step_begin(void* state, uint64_t seed_base, void* stream);
+/* background != 0 (here and in c2dsr_adamw_amsgrad_peer): the launch runs beside higher-priority work -- short-lived
+ * CTAs instead of a resident grid-stride grid. */
 int c2dsr_adamw_amsgrad_dyn(const c2dsr_adam_tensor* table_dev, int n_tensors, int64_t max_n, const void* state,
-                            float beta1, float beta2, float eps, float weight_decay, void* stream);
+                            float beta1, float beta2, float eps, float weight_decay, int background, void* stream);
 
 /* Data-parallel form of the same update over peer memory (NVLink / NVSwitch), one launch: the gradients of the large
  * tensors live at the same offsets of a "gradient block" on every rank, the parameters of a "parameter block"; all
@@ -367,7 +369,7 @@ typedef struct {
 } c2dsr_peer_map;
 int c2dsr_adamw_amsgrad_peer(const c2dsr_peer_tensor* table_dev, int n_tensors, int64_t max_n,
                              const c2dsr_peer_map* map, const void* state, float beta1, float beta2, float eps,
-                             float weight_decay, void* stream);
+                             float weight_decay, int background, void* stream);
 
 /* elementwise glue: out = a*x + b*y (y may be NULL) */
 int c2dsr_axpby(const float* x, const float* y, float* out, int64_t n, float a, float b, void* stream);

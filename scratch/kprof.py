@@ -57,6 +57,10 @@ allv = sorted([e for e in ev if e.time_range.start >= t00], key=lambda e: e.time
 for e in allv:
     if e.time_range.start - t00 > 520: break
     print(f"S{getattr(e, 'device_resource_id', 0):<4d} {e.time_range.start - t00:8.1f} {e.device_time:7.1f}  {e.name[:60]}")
+print("---- all streams, last step, kernels >= 12 us (stream, start, dur, name)")
+for e in allv:
+    if e.device_time >= 12:
+        print(f"S{getattr(e, 'device_resource_id', 0):<4d} {e.time_range.start - t00:8.1f} {e.device_time:7.1f}  {e.name[:70]}")
 print("per-stream busy us/step:", {k: (v[0] / N, round(v[1] / N, 1)) for k, v in by_stream.items()})
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
     print(f"{v[1]/N:9.1f} us  x{v[0]/N:5.1f}  {k}")
