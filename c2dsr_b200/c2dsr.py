@@ -75,6 +75,10 @@ class SelfAttention(nn.Module):
                                    *self.weights())
 
 
+import os as _os
+_PRIO = -1 if _os.environ.get("C2DSR_STEP_PRIO", "1") != "0" else 0
+
+
 class C2DSR(nn.Module):
     def __init__(self, args, adj, adj_specific):
         super().__init__()
@@ -202,7 +206,7 @@ class C2DSR(nn.Module):
             return hs[ar, sel_share], hx[ar, sel_a], hy[ar, sel_b]
         cur = torch.cuda.current_stream()
         if self._side is None or len(self._side) < 2:
-            self._side = tuple(torch.cuda.Stream(priority=-1) for _ in range(2))
+            self._side = tuple(torch.cuda.Stream(priority=_PRIO) for _ in range(2))
         jobs = ((self.attn_share, self.embed_i, self.hi_share, seq_share, pos_share, sel_share, None),
                 (self.attn_a, self.embed_i_a, self.hi_a, seq_a, pos_a, sel_a, self._side[0]),
                 (self.attn_b, self.embed_i_b, self.hi_b, seq_b, pos_b, sel_b, self._side[1]))
@@ -256,7 +260,7 @@ class C2DSR(nn.Module):
         """Independent branches forked onto side streams inside one autograd node (ops.BranchSetFn); the
         first branch stays on the caller's stream."""
         if self._side is None or len(self._side) < len(branches) - 1:
-            self._side = tuple(torch.cuda.Stream(priority=-1) for _ in range(len(branches) - 1))
+            self._side = tuple(torch.cuda.Stream(priority=_PRIO) for _ in range(len(branches) - 1))
         grad = torch.is_grad_enabled()
         specs, flat = [], []
         for attn, table, hi, seq, pos, tag in branches:

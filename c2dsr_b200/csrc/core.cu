@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/c2dsr_b200.h"
 
@@ -247,7 +248,7 @@ __device__ __forceinline__ void peer_st(float* addr, float4 v) {
                  :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <bool MC>
+template <bool MC, int U>
 __global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor* __restrict__ table,
                                                          const __grid_constant__ c2dsr_peer_map map, float beta1,
                                                          float beta2, float eps, float wd,
@@ -307,14 +308,16 @@ __global__ void __launch_bounds__(256) adamw_peer_kernel(const c2dsr_peer_tensor
             for (int k = 0; k < map.world; ++k) peer_st(map.param[k] + e, p);
         }
     };
-    // four remote fetches in flight per thread before the first is consumed (NVLink round trips are microseconds)
+    // U remote fetches in flight per thread before the first is consumed (NVLink round trips are microseconds)
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < n4; i += 4 * stride) {
-        const float4 g0 = fetch(i), g1 = fetch(i + stride), g2 = fetch(i + 2 * stride), g3 = fetch(i + 3 * stride);
-        apply(i, g0);
-        apply(i + stride, g1);
-        apply(i + 2 * stride, g2);
-        apply(i + 3 * stride, g3);
+    if (U == 4) {
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            const float4 g0 = fetch(i), g1 = fetch(i + stride), g2 = fetch(i + 2 * stride), g3 = fetch(i + 3 * stride);
+            apply(i, g0);
+            apply(i + stride, g1);
+            apply(i + 2 * stride, g2);
+            apply(i + 3 * stride, g3);
+        }
     }
     for (; i < n4; i += stride) apply(i, fetch(i));
 }
@@ -438,12 +441,18 @@ int c2dsr_adamw_amsgrad_peer(const c2dsr_peer_tensor* table_dev, int n_tensors, 
     const int64_t chunks = adam_chunks(max_n, background ? 256 * 16 : 256 * 4, background);
     const dim3 grid((unsigned)chunks, (unsigned)n_tensors);
     const auto* st = reinterpret_cast<const c2dsr_step_state*>(state);
-    if (map->grad_mc != nullptr && map->param_mc != nullptr)
-        adamw_peer_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, *map, beta1, beta2, eps,
-                                                                       weight_decay, st);
-    else
-        adamw_peer_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, *map, beta1, beta2, eps,
-                                                                        weight_decay, st);
+    // remote fetches in flight per thread: measured on B200s, 2 ranks 3.21 (1) vs 3.28 ms (4) per step, 4 ranks 3.46 (1)
+    // vs 3.42 ms (4) -- the more peers, the longer the round trips that have to be covered
+    static const int forced = [] { const char* e = getenv("C2DSR_DP_UNROLL"); return e ? atoi(e) : 0; }();
+    const int unroll = forced ? forced : (map->world <= 2 ? 1 : 4);
+    const bool mc = map->grad_mc != nullptr && map->param_mc != nullptr;
+    auto launch = [&](auto kernel) {
+        kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table_dev, *map, beta1, beta2, eps, weight_decay, st);
+    };
+    if (mc && unroll == 4) launch(adamw_peer_kernel<true, 4>);
+    else if (mc) launch(adamw_peer_kernel<true, 1>);
+    else if (unroll == 4) launch(adamw_peer_kernel<false, 4>);
+    else launch(adamw_peer_kernel<false, 1>);
     note_launches(1);
     return check_launch("adamw_amsgrad_peer");
 }

@@ -352,7 +352,8 @@ class ShardedStep:
                 if not staged:
                     self._peer_stage(st)
                 self._peer_barrier(1 + st["idx"])            # every rank's gradient of this tensor is in place
-                self._peer_update([st], stream, background=True)
+                # (short-lived "background" CTAs measured slower here: 3.36 vs 3.29 ms per step on 2 GPUs)
+                self._peer_update([st], stream, background=os.environ.get("C2DSR_DP_BG", "0") != "0")
             st["done"] = True
             return
         self._reduce(st, stream)

@@ -11,6 +11,7 @@ torch semantics) or in a sum owned by the optimiser (``accumulate=True``, see th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -104,7 +105,7 @@ class FusedAdamW(torch.optim.Optimizer):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             call("c2dsr_adamw_amsgrad_dyn", ptr(e["table"]), 1, p.numel(), ptr(self.dyn_state), b1, b2, group["eps"],
-                 group["weight_decay"], 1, side.cuda_stream)
+                 group["weight_decay"], int(os.environ.get("C2DSR_ADAM_BG", "1") != "0"), side.cuda_stream)
         e["done"] = True
 
     def attach_step_state(self, state: torch.Tensor):

@@ -344,7 +344,8 @@ class Trainer(object):
         # the step's own chain (and the model's branch streams) at high priority, the optimiser pipelines that run
         # beside the backward at the default, lowest one: their CTAs fill what the chain leaves free
         if self._step_stream is None:
-            self._step_stream = torch.cuda.Stream(priority=-1)
+            import os
+            self._step_stream = torch.cuda.Stream(priority=-1 if os.environ.get("C2DSR_STEP_PRIO", "1") != "0" else 0)
         try:
             with torch.cuda.graph(graph, stream=self._step_stream):
                 self.model.convolve_graph(lazy=True)
