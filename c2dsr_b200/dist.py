@@ -232,11 +232,13 @@ class ShardedStep:
         if ok.item() == 0:
             return
         block.zero_()
-        # multicast (multimem.ld_reduce / multimem.st, C2DSR_DP=multimem) moves (1 + 1 / world) x the bytes per
-        # NVLink direction, plain peer loads / stores 2 (world - 1) / world x -- yet measured on 2 and 4 B200s the
-        # peer loads / stores are faster (4 GPUs: 3.36 vs 3.47 ms per step), and they sum in rank order, so the
-        # result does not depend on the switch: they are the default
-        want_mc = os.environ.get("C2DSR_DP", "peer") == "multimem"
+        # multicast (multimem.ld_reduce / multimem.st: the NVSwitch adds the copies and replicates the stores) moves
+        # (1 + 1 / world) x the bytes per NVLink direction, plain peer loads / stores 2 (world - 1) / world x.
+        # Measured on B200s (ms per step): 2 ranks 3.23 peer vs 3.97 multimem, 4 ranks 3.36 vs 3.47, 8 ranks 3.68 vs
+        # 3.33 -- peer loads / stores (summed in rank order) up to 7 ranks, multicast from 8 on.
+        # C2DSR_DP=p2p | multimem forces one of them.
+        mode = os.environ.get("C2DSR_DP", "peer")
+        want_mc = mode == "multimem" or (mode != "p2p" and self.world_size >= 8)
         mc = int(hdl.multicast_ptr) if want_mc and getattr(hdl, "has_multicast_support", False) else 0
         pmap = PeerMap()
         pmap.world, pmap.rank = self.world_size, self.rank
