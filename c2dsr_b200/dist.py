@@ -3,9 +3,15 @@ box, gloo in the CPU tests).  The path has exactly two exchange steps (SURVEY.md
 
 * training  -- data-parallel: the global batch is split across ranks, parameters and graph are
   replicated; per step one tiny all-reduce (valid-target counts and rows, so that loss normalisers
-  equal the single-GPU ones), then a sharded optimiser step (``FlatShards``): the fp32 gradients are
-  reduce-scattered, every rank runs AdamW on its 1/world of one flat parameter buffer, and the
-  updated shards are all-gathered (same bytes on the wire as one all-reduce);
+  equal the single-GPU ones), then a sharded optimiser step (``ShardedStep``): every rank updates
+  1 / world of every tensor.  On NVLink-connected GPUs this runs over peer memory -- gradients and
+  parameters of all ranks live in symmetric, peer-mapped blocks, and per tensor ONE kernel sums the
+  gradient copies, applies AdamW to this rank's slice and stores the result into every rank's
+  parameters (peer loads / stores, or multimem through the NVSwitch), bracketed by device-side
+  barriers; otherwise per-tensor NCCL pipelines (reduce-scatter -> AdamW slice -> all-gather) and a
+  flat bucket for the small tensors (``FlatShards``).  The optimiser moments of a tensor exist only
+  as the slices their owners hold (``ShardedStep.big[i]["m" | "v" | "vmax" | "gsum"]``); like the
+  reference, nothing is checkpointed;
 * evaluation -- each rank encodes its slice of the query batch and the query vectors are
   all-gathered (2 MB); the item catalogue is sharded by rows of the classifier; the target score
   comes from the owning shard (sum all-reduce with zeros elsewhere, exact) and the per-shard partial
