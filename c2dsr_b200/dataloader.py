@@ -157,19 +157,41 @@ def _flatten(seqs: Sequence[Sequence[int]], len_max: int):
     return items, offs
 
 
+def train_draws(items: np.ndarray, offs: np.ndarray, n_item_a: int, n_item_b: int, rng=random) -> np.ndarray:
+    """The corruption draws of the training split, one per input position in sequence order (the final target of a
+    sequence gets none): ``randint(0, n_item_a - 1)`` where the position holds a domain-A item, else
+    ``randint(n_item_a, n_item_a + n_item_b - 1)`` (dataloader.py:80,85).  The reference draws for every sequence,
+    kept or dropped, so the stream position after a split matches too."""
+    pad = n_item_a + n_item_b
+    is_input = np.ones(len(items), bool)
+    if len(offs) > 1:
+        is_input[offs[1:] - 1] = False
+    dom_a = (items[is_input] < n_item_a).tolist()
+    randint, a_hi, b_lo, b_hi = rng.randint, n_item_a - 1, n_item_a, pad - 1
+    return np.fromiter((randint(0, a_hi) if a else randint(b_lo, b_hi) for a in dom_a), np.int64, len(dom_a))
+
+
+def eval_picks(items: np.ndarray, offs: np.ndarray, n_item_a: int, n_item_b: int, n_neg_sample: int,
+               rng=random) -> np.ndarray:
+    """[n, n_neg] samples of range(population) per evaluation sequence (dataloader.py:216-224): the population is the
+    target's domain without the target (domain B: range(n_item_b - n_item_a), Q7b); shifting the picks past the
+    target (done on the device) gives the reference's negatives."""
+    n = len(offs) - 1
+    last = items[offs[1:] - 1] if n else np.zeros(0, np.int64)
+    g = np.where(last < n_item_a, last, last - n_item_a)
+    hi = np.where(last < n_item_a, n_item_a, n_item_b - n_item_a)
+    n_pop = (g + np.maximum(0, hi - g - 1)).tolist()
+    sample = rng.sample
+    return np.asarray([sample(range(p), n_neg_sample) for p in n_pop], np.int64).reshape(n, n_neg_sample)
+
+
 def preprocess_train_device(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int, device,
                             rng=random) -> torch.Tensor:
     """``preprocess_train`` with the per-sequence work on the GPU ([n_kept, 14, len_max] int64 on ``device``).  The
-    host keeps only what has to follow Python's ``random`` stream: one ``randint`` per input position, in the
-    reference's order (dataloader.py:80,85); note that the reference draws for every sequence, kept or not."""
+    host keeps only what has to follow Python's ``random`` stream (``train_draws``)."""
     from . import ops
-    pad = n_item_a + n_item_b
     items, offs = _flatten(seqs, len_max)
-    is_input = np.ones(len(items), bool)
-    is_input[offs[1:] - 1] = False                       # the final target of every sequence gets no draw
-    dom_a = (items[is_input] < n_item_a).tolist()
-    randint, a_hi, b_lo, b_hi = rng.randint, n_item_a - 1, n_item_a, pad - 1
-    draws = np.fromiter((randint(0, a_hi) if a else randint(b_lo, b_hi) for a in dom_a), np.int64, len(dom_a))
+    draws = train_draws(items, offs, n_item_a, n_item_b, rng)
     dev = torch.device(device)
     fields, keep = ops.preprocess_train(torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev),
                                         torch.from_numpy(draws).to(dev), n_item_a, n_item_b, len_max)
@@ -179,15 +201,10 @@ def preprocess_train_device(seqs: Sequence[Sequence[int]], n_item_a: int, n_item
 def preprocess_evaluate_device(seqs: Sequence[Sequence[int]], n_item_a: int, n_item_b: int, len_max: int,
                                n_neg_sample: int, device, rng=random):
     """``preprocess_evaluate`` with the per-sequence work on the GPU; the host draws ``rng.sample`` per sequence
-    (dataloader.py:216-224) and nothing else."""
+    (``eval_picks``) and nothing else."""
     from . import ops
     items, offs = _flatten(seqs, len_max)
-    last = items[offs[1:] - 1] if len(seqs) else np.zeros(0, np.int64)
-    g = np.where(last < n_item_a, last, last - n_item_a)
-    hi = np.where(last < n_item_a, n_item_a, n_item_b - n_item_a)
-    n_pop = (g + np.maximum(0, hi - g - 1)).tolist()
-    sample = rng.sample
-    picks = np.asarray([sample(range(p), n_neg_sample) for p in n_pop], np.int64).reshape(len(seqs), n_neg_sample)
+    picks = eval_picks(items, offs, n_item_a, n_item_b, n_neg_sample, rng)
     dev = torch.device(device)
     return ops.preprocess_eval(torch.from_numpy(items).to(dev), torch.from_numpy(offs).to(dev),
                                torch.from_numpy(picks).to(dev), n_item_a, n_item_b, len_max)

@@ -108,3 +108,42 @@ def test_metrics_equal_oracle():
                                oracle.cal_score(ra, rb, metrics.BENCHMARKS["fk"]), rtol=1e-14)
     with pytest.raises(ZeroDivisionError):
         metrics.cal_metrics([])
+
+
+def test_device_preprocessor_host_half_follows_the_reference_stream():
+    """The draws the device preprocessor takes as input (dataloader.train_draws / eval_picks) are the ones the
+    reference's preprocessing consumed: recovered from the golden fields the reference wrote (corrupted sequences,
+    negatives) and from the host restatement on ragged synthetic logs, including the stream position afterwards."""
+    g = Golden("mid_default")
+    hp = g.hp
+    na, nb, L = hp["n_item_a"], hp["n_item_b"], hp["len_max"]
+    random.seed(hp["seed"])
+    seqs = g.raw("train")
+    items, offs = dl._flatten(seqs, L)
+    draws = dl.train_draws(items, offs, na, nb)
+    # sequences the reference kept, in order: its seq_share_neg_a / _b hold the draw at every input position
+    fields = g.z["train_fields"]
+    kept = [u for u in seqs if len(dl.preprocess_train([u], na, nb, L, rng=random.Random(0)))]
+    assert len(kept) == len(fields)
+    pos = {id(u): int(offs[i]) - i for i, u in enumerate(seqs)}
+    for row, u in zip(fields, kept):
+        m = len(u) - 1
+        seq = np.asarray(u[:-1])
+        want = np.where(seq < na, row[13][L - m:], row[12][L - m:])        # A position: neg_b holds the draw
+        assert np.array_equal(draws[pos[id(u)]:pos[id(u)] + m], want)
+    for mode in ("val", "test"):                                            # same stream, continued
+        ev = g.raw(mode)
+        items, offs = dl._flatten(ev, L)
+        picks = dl.eval_picks(items, offs, na, nb, hp["n_neg_sample"])
+        gt = g.z[f"{mode}_four"][:, 3:4]
+        assert np.array_equal(np.where(picks < gt, picks, picks + 1), g.z[f"{mode}_neg"])
+    # ragged synthetic log: same consumption as the host restatement
+    r = np.random.RandomState(5)
+    logs = [r.randint(0, 40, int(r.randint(1, 9))).tolist() for _ in range(200)]
+    a, b = random.Random(3), random.Random(3)
+    dl.preprocess_train(logs, 17, 23, 7, rng=a)
+    items, offs = dl._flatten(logs, 7)
+    assert len(dl.train_draws(items, offs, 17, 23, rng=b)) == len(items) - len(logs)
+    assert a.random() == b.random()
+    with pytest.raises(ValueError):
+        dl._flatten([[1] * 10], 7)
