@@ -171,6 +171,33 @@ def test_train_step_matches_reference(name):
         assert rel_err(got, ref) < 1e-3, k
 
 
+@pytest.mark.parametrize("name", ["mid_default", "tiny_prenorm_shared"])
+def test_early_optimiser_steps_are_bit_identical(name):
+    """Updating the large tensors beside the backward (FusedAdamW.enable_early: classifier matrices from their
+    post-accumulate-grad hook, embedding tables from inside their branch's backward, gradients in persistent sinks)
+    is the same arithmetic in a different launch order: after eager steps, the capture and replays -- with dropout on
+    -- every parameter and every per-epoch gradient sum equals the end-of-backward update bit for bit."""
+    g = Golden(name)
+    states = []
+    for early in (1, 0):
+        tr = _trainer_from_golden(g, early_adam=early, dropout_gnn=0.2, dropout_attn=0.2)
+        assert bool(getattr(tr.optimizer, "_early", None)) == bool(early)
+        tr.model.train()
+        tr.optimizer.zero_grad()
+        losses = [[float(x) for x in tr.train_step(g.train_batch(s))] for s in range(len(g.z["losses"]))]
+        named = dict(tr.model.named_parameters())
+        states.append((losses, {k: p.detach().cpu().clone() for k, p in named.items()},
+                       {k: tr.optimizer.accumulated_grad(p).cpu().clone() for k, p in named.items()
+                        if tr.optimizer.accumulated_grad(p) is not None}))
+    (l1, p1, a1), (l0, p0, a0) = states
+    assert l1 == l0
+    assert p1.keys() == p0.keys() and a1.keys() == a0.keys()
+    for k in p1:
+        assert torch.equal(p1[k], p0[k]), k
+    for k in a1:
+        assert torch.equal(a1[k], a0[k]), k
+
+
 def test_run_epoch_and_run_test_contract():
     """Trainer.run_epoch / run_test return two python lists of int ranks (trainer.py:40-83)."""
     g = Golden("tiny_default")
