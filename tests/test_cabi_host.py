@@ -161,3 +161,39 @@ def test_header_is_plain_c():
                 ["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_struct_layouts_match_the_ctypes_mirror(tmp_path):
+    """The structs that cross the boundary by value or as device tables (c2dsr_adam_tensor, c2dsr_peer_tensor,
+    c2dsr_peer_map) have the same size and field offsets in C as in c2dsr_b200/_cabi.py."""
+    import ctypes
+    import shutil
+    import subprocess
+    from c2dsr_b200 import _cabi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "layout.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "c2dsr_b200.h"
+int main(void) {
+    printf("%zu %zu %zu %zu\\n", sizeof(c2dsr_adam_tensor), offsetof(c2dsr_adam_tensor, acc),
+           offsetof(c2dsr_adam_tensor, vmax), offsetof(c2dsr_adam_tensor, n));
+    printf("%zu %zu\\n", sizeof(c2dsr_peer_tensor), offsetof(c2dsr_peer_tensor, offset));
+    printf("%zu %zu %zu %zu %zu %d\\n", sizeof(c2dsr_peer_map), offsetof(c2dsr_peer_map, grad),
+           offsetof(c2dsr_peer_map, param), offsetof(c2dsr_peer_map, grad_mc), offsetof(c2dsr_peer_map, param_mc),
+           C2DSR_MAX_PEERS);
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [[int(x) for x in line.split()] for line in subprocess.run([str(exe)], capture_output=True,
+                                                                      text=True).stdout.strip().splitlines()]
+    A, P, M = _cabi.AdamTensor, _cabi.PeerTensor, _cabi.PeerMap
+    assert got[0] == [ctypes.sizeof(A), A.acc.offset, A.vmax.offset, A.n.offset]
+    assert got[1] == [ctypes.sizeof(P), P.offset.offset]
+    assert got[2] == [ctypes.sizeof(M), M.grad.offset, M.param.offset, M.grad_mc.offset, M.param_mc.offset,
+                      _cabi.MAX_PEERS]
