@@ -128,3 +128,34 @@ def test_shard_bounds_partition():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
             assert all(hi >= lo for lo, hi in b)
+
+
+def test_flat_shards_rebase_and_stage():
+    """FlatShards.rebase moves the flat parameter buffer / gradient bucket into caller-supplied storage (the symmetric
+    block of the peer-memory step): values preserved, parameters become views of the new buffer, padding stays zero;
+    stage_grads copies the step's gradients into the bucket and writes zeros for a parameter without one."""
+    from c2dsr_b200.dist import FlatShards
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((5, 3), (7,), (2, 2, 2))]
+    before = [p.detach().clone() for p in params]
+    fs = FlatShards(params, rank=1, world_size=2)
+    n = fs.flat.numel()
+    assert n == 2 * fs.shard and fs.shard % FlatShards.ALIGN == 0
+    block = torch.full((2 * n,), 7.0)
+    fs.rebase(block[:n], block[n:])
+    assert fs.flat.data_ptr() == block.data_ptr() and fs.bucket.data_ptr() == block[n:].data_ptr()
+    for p, b, off in zip(params, before, fs.offsets):
+        assert torch.equal(p.detach(), b)
+        assert p.data_ptr() == block[off:].data_ptr()                 # a view of the new buffer
+    used = sum(p.numel() for p in params)
+    assert float(fs.flat.abs().sum()) == float(sum(b.abs().sum() for b in before))   # padding copied as zeros
+    assert float(block[n:].abs().sum()) == 0.0                                       # bucket cleared
+    assert fs.param_shard.data_ptr() == block[fs.shard:].data_ptr() and fs.param_shard.numel() == fs.shard
+    params[0].grad = torch.ones(5, 3)
+    params[2].grad = torch.full((2, 2, 2), 2.0)                       # params[1] got no gradient this step
+    fs.stage_grads()
+    assert float(fs.bucket.sum()) == 15.0 + 16.0 and used == 30
+    assert torch.equal(fs.views[1], torch.zeros(7))
+    # an update through the flat buffer is an update of the parameters
+    fs.flat.add_(1.0)
+    assert torch.equal(params[1].detach(), before[1] + 1.0)
